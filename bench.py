@@ -1,0 +1,282 @@
+#!/usr/bin/env python
+"""bench.py — sampled backbone residues/sec (N=256, 500 denoise steps) on N GPUs of one node.
+
+  python bench.py --gpus 1 --steps K --warmup W            (our arm, default)
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+         bench.py --gpus N --steps K --warmup W            (one rank per GPU, NCCL)
+  python bench.py --impl reference ...                     (the reference's CPU path = oracle port, host cores)
+
+A "step" is one pass of the hot path over one batch: the whole reverse-diffusion sampling of B backbones per GPU
+(prior draw -> 1 self-conditioning forward + (num_t-1) x [ScoreNetwork.forward + SE3Diffuser.reverse] + final forward ->
+atom37), i.e. Experiment.inference_fn (experiments/train_se3_diffusion.py:718-818 of the reference) for that batch.
+value = backbones x residues / step time, whole job (all GPUs).  Weak scaling: per-GPU batch fixed.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "sampled backbone residues/sec (N=256, 500 denoise steps)"
+
+
+def parse():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=2)
+    p.add_argument("--warmup", type=int, default=3)
+    p.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    p.add_argument("--batch", type=int, default=None, help="backbones per GPU (default: 32 = BASELINE config 3's per-GPU shard)")
+    p.add_argument("--nres", type=int, default=256)
+    p.add_argument("--num-t", type=int, default=500)
+    p.add_argument("--precision", default=None, choices=[None, "fp32", "bf16x3", "bf16"])
+    p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--cpu-steps", type=int, default=2, help="denoise steps of the bounded CPU sample")
+    return p.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"], "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                "source": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_baseline(nres, num_t, cpu_steps, state):
+    """Bounded sample of the same workload on the host cores through the oracle port (kind "port"): 1 backbone x nres,
+    the priming forward + `cpu_steps` denoise steps, extrapolated to the 501 forwards of a num_t-step sample."""
+    import torch
+    from oracle import framediff_oracle as fo
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    w = fo.as_torch_weights(state)
+    np.random.seed(123)
+    fo.igso3_row(fo.so3_t_to_idx(1.0))        # warm the IGSO(3) row cache (the reference's 52 s cache build is excluded too)
+    r7 = fo.sample_ref(nres)[None]
+    feats = fo.init_feats(r7)
+    t0 = time.perf_counter()
+    fo.inference_loop(w, feats, num_t=num_t, min_t=0.01, noise_scale=0.1, max_steps=cpu_steps)
+    dt = time.perf_counter() - t0
+    per_fwd = dt / (cpu_steps + 1)
+    full = per_fwd * (num_t + 1)
+    return {"value": nres / full, "unit": "residues/s", "cores": cores, "kind": "port",
+            "sample": f"1 backbone x N={nres}: self-conditioning forward + {cpu_steps} of {num_t} denoise steps in {dt:.2f} s "
+                      f"({per_fwd:.3f} s per forward+reverse), extrapolated x{num_t + 1}",
+            "seconds_measured": dt}
+
+
+def synthetic_state():
+    from oracle import framediff_oracle as fo      # weights only (deterministic random init of the architecture)
+    return fo.synthetic_weights(0)
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path (oracle port; /root/reference does not exist on
+    the GPU box), all host threads.  Under torchrun only rank 0 works."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    state = synthetic_state()
+    times = []
+    last = None
+    for i in range(args.warmup + args.steps):
+        last = cpu_baseline(args.nres, args.num_t, args.cpu_steps, state)
+        if i >= args.warmup:
+            times.append(last["value"])
+    v = float(np.mean(times))
+    cb = dict(last); cb["value"] = v
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "residues/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * args.nres / v, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic (random-init weights, Gaussian/IGSO(3) prior noise)",
+            "config": {"workload": f"1 backbone x N={args.nres} x {args.num_t} denoise steps per step, CPU (bounded sample, extrapolated)",
+                       "nres": args.nres, "num_t": args.num_t},
+            "cpu_baseline": cb, "e2e": {"value": v, "unit": "residues/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+    import torch
+    import torch.distributed as dist
+    from se3_diffusion_b200 import FrameDiffEngine
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if world != args.gpus and rank == 0:
+        print(f"[bench] warning: --gpus {args.gpus} but WORLD_SIZE={world}", file=sys.stderr)
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    B = args.batch or 32
+    N, T = args.nres, args.num_t
+    prec = args.precision or os.environ.get("FD_PRECISION", "fp32")
+    eng = FrameDiffEngine(local, prec)
+    state = synthetic_state()
+    eng.load_weights(state)
+    first = rank * B
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    gathered = torch.empty(world * B, N, 37, 3, device=dev) if world > 1 else None
+
+    def device_step(seed):
+        """inputs resident in HBM: prior drawn on the device, final coordinates stay in HBM (+ NCCL gather for N>1)."""
+        a37, rig, ms, nl = eng.sample_device(B, N, num_t=T, seed=seed, first_sample=first)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, a37)
+        return ms, nl
+
+    masks = {"res_mask": np.ones((B, N), np.float32), "fixed_mask": np.zeros((B, N), np.float32),
+             "seq_idx": np.tile(np.arange(1, N + 1, dtype=np.int32), (B, 1))}
+
+    def e2e_step(seed):
+        """public API with HOST buffers: init features H2D, final atom37/rigids/psi D2H into pinned memory."""
+        out = eng.sample(B, N, num_t=T, seed=seed, first_sample=first, **masks)
+        return out
+
+    # ---- warm-up ----------------------------------------------------------------------------------------------------
+    for i in range(args.warmup):
+        device_step(1000 + i)
+    barrier()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    # ---- timed: device-resident ---------------------------------------------------------------------------------------
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t_wall0 = time.perf_counter()
+    gpu_ms, launches = 0.0, 0
+    for i in range(args.steps):
+        ms, nl = device_step(2000 + i)
+        gpu_ms += ms; launches += nl
+    barrier()
+    wall = time.perf_counter() - t_wall0
+    # the loop runs on the engine's own stream and is timed there with CUDA events (fd_sample_dev's gpu_ms); wall adds the
+    # host-side graph capture/launch overhead and, for N>1, the NCCL gather — report the larger (honest) one.
+    t = torch.tensor([max(wall, gpu_ms / 1e3)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    step_s = float(t.item()) / args.steps
+    # ---- timed: end-to-end through the host API --------------------------------------------------------------------------
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        e2e_step(3000 + i)
+    barrier()
+    te = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_s = float(te.item()) / args.steps
+    clk = clocks.stop() if rank == 0 else None
+
+    # ---- roofline of the dominant kernel: EdgeTransition (87 % of the reference's FLOPs) ----------------------------------
+    roof = None
+    if rank == 0:
+        from oracle import framediff_oracle as fo
+        pk = peaks()
+        np.random.seed(0)
+        r7 = torch.stack([fo.sample_ref(N) for _ in range(min(B, 4))]).repeat((B + 3) // 4, 1, 1)[:B]
+        f = fo.init_feats(r7); f["t"] = torch.full((B,), 0.5)
+        eng.forward(f, want_atoms=False); torch.cuda.synchronize(dev)
+        eng.stage_timing(True)
+        reps = 3
+        for _ in range(reps):
+            eng.forward(f, want_atoms=False)
+        torch.cuda.synchronize(dev)
+        st = eng.stage_times()
+        eng.stage_timing(False)
+        et_ms = st["edge_transition"][0] / reps / 3            # per EdgeTransition layer (3 per forward)
+        flops_layer = 524288.0 * B * N * N                     # executed FLOP/edge: 2*(128*384 + 384*384 + 512*128)
+        ach = flops_layer / (et_ms * 1e-3) / 1e12
+        fwd_ms = sum(v[0] for v in st.values()) / reps
+        roof = {"bound": "tensor", "kernel": "edge_transition (fused 3-GEMM MLP + LayerNorm, one launch group per layer)",
+                "achieved": ach, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": ach / pk["bf16_tflops_sustained"],
+                "peak_source": pk["source"] + ", sustained bf16 figure (kernel timed inside a long step)",
+                "traffic": None, "ms_per_launch_group": et_ms, "algorithmic_flops_per_launch_group": flops_layer,
+                "share_of_forward": st["edge_transition"][0] / reps / fwd_ms,
+                "stage_ms_per_forward": {k: v[0] / reps for k, v in st.items()}}
+
+    if rank == 0:
+        value = world * B * N / step_s
+        e2e_v = world * B * N / e2e_s
+        cb = None if args.no_cpu_baseline else cpu_baseline(N, T, args.cpu_steps, state)
+        line = {"metric": METRIC, "value": value, "unit": "residues/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": step_s * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": {"fp32": "f32", "bf16x3": "bf16x3 (split bf16, fp32 accumulate)", "bf16": "bf16"}[prec],
+                "data": "synthetic (random-init weights of the FrameDiff architecture; Philox Gaussian/IGSO(3) prior + step noise)",
+                "config": {"workload": f"{B} backbones/GPU x N={N} residues x {T} denoise steps (BASELINE config 3 per-GPU shard)",
+                           "batch_per_gpu": B, "global_batch": world * B, "nres": N, "num_t": T, "precision": prec,
+                           "parallelism": f"batch-sharded dp{world}", "cuda_graph": True,
+                           "l2": "not flushed: each forward streams a %.0f MB edge tensor (> 126 MB L2)" % (B * N * N * 128 * 4 / 1e6)},
+                "e2e": {"value": e2e_v, "unit": "residues/s", "ms_per_step": e2e_s * 1e3,
+                        "h2d_bytes_per_step": int(sum(v.nbytes for v in masks.values())),
+                        "d2h_bytes_per_step": int(B * N * (111 + 7 + 2) * 4)},
+                "gpu_launches": int(launches), "gpu_ms_per_step_events": gpu_ms / args.steps,
+                "clocks": clk, "roofline": roof, "cpu_baseline": cb}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,193 @@
+/*
+ * framediff_b200.h — C ABI of libframediff_b200.so: the B200-native FrameDiff hot path.
+ *
+ * The reference (jasonkyuyim/se3_diffusion) is pure Python: it has no FFI / operator interface of its own.  Its
+ * seam for this path is the import-level API
+ *     model.score_network.ScoreNetwork.forward             (/root/reference/model/score_network.py:170-215)
+ *     data.se3_diffuser.SE3Diffuser.{sample_ref,reverse,forward_marginal,score,calc_rot_score,calc_trans_score}
+ *                                                          (/root/reference/data/se3_diffuser.py:43-268)
+ *     data.all_atom.compute_backbone                       (/root/reference/data/all_atom.py:152-174)
+ *     experiments.train_se3_diffusion.Experiment.inference_fn (…/experiments/train_se3_diffusion.py:718-818)
+ * Each entry point below states which of those it replaces.  The Python overlay modules in
+ * se3_diffusion_b200/overlay/ bind these symbols with ctypes and re-export the reference's class names, so the
+ * reference drivers run unchanged.
+ *
+ * Conventions
+ *   - plain C types only: raw pointers + sizes; no torch / C++ types cross the boundary;
+ *   - every function returns 0 on success, a negative FD_E* code on failure; fd_last_error() gives the message;
+ *   - "dev" pointers are CUDA device pointers on the handle's device, "host" pointers are host memory;
+ *   - all tensors are dense row-major (C order), batch first; B = backbones in the batch, N = residues;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = the CUDA default stream); device-API calls are
+ *     asynchronous on it; the whole-loop calls (fd_sample_*) run on the handle's own stream and synchronise
+ *     before returning;
+ *   - one handle per (process, device); a handle is not thread-safe (the reference is single-threaded Python).
+ */
+#ifndef FRAMEDIFF_B200_H
+#define FRAMEDIFF_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct fd_context* fd_handle;
+
+enum {
+  FD_OK = 0,
+  FD_EINVAL = -1,   /* bad argument (shape, null pointer, t outside [0,1], …) — the reference raises ValueError */
+  FD_ECUDA = -2,    /* CUDA runtime / driver error */
+  FD_ENOMEM = -3,   /* device allocation failed */
+  FD_ESTATE = -4    /* call order (weights not loaded, …) */
+};
+
+/* GEMM operand precision of the edge-tensor kernels (EdgeTransition / edge embedder).  Everything else is fp32
+ * (frames, points, softmax statistics) or fp64 (IGSO(3) series, reverse step). */
+enum {
+  FD_PREC_FP32 = 0,      /* CUDA-core fp32 everywhere (exact-parity mode) */
+  FD_PREC_BF16X3 = 1,    /* tcgen05 bf16 tensor cores, 3-term split (hi·hi + hi·lo + lo·hi), fp32 accumulate */
+  FD_PREC_BF16 = 2       /* tcgen05 bf16 tensor cores, single term, fp32 accumulate (throughput mode) */
+};
+
+const char* fd_last_error(void);
+const char* fd_version(void);
+
+/* ---- lifetime ------------------------------------------------------------------------------------------- */
+int fd_create(fd_handle* out, int device);
+int fd_destroy(fd_handle h);
+int fd_set_precision(fd_handle h, int prec);
+int fd_get_precision(fd_handle h);
+
+/* ---- parameters: the reference's 282-entry state_dict, fp32 ------------------------- */
+int fd_num_params(void);
+const char* fd_param_name(int i);
+int fd_param_ndim(int i);
+int64_t fd_param_dim(int i, int d);
+int64_t fd_param_numel(int i);
+/* host_ptrs[i] -> fp32 host array of parameter i (schema order).  Packs / transposes / splits into the device arena.
+ * Replaces ScoreNetwork.load_state_dict (experiments/inference_se3_diffusion.py:151-154). */
+int fd_load_weights(fd_handle h, const float* const* host_ptrs);
+
+/* ---- ScoreNetwork.forward (model/score_network.py:170-215) -------------------------------------------------- */
+typedef struct {
+  const float* rigids_t;        /* [B,N,7] (qw,qx,qy,qz,tx,ty,tz), Å */
+  const double* t;              /* [B] diffusion time in [0,1], widened to float64 */
+  int t_is_f32;                 /* 1: the caller's t tensor was fp32 (Experiment.inference_fn): t*1e4 and the R^3 score are
+                                   then evaluated in fp32 like the reference; 0: t was float64 (numpy-born features) */
+  const double* sigma;          /* [B] IGSO(3) sigma already quantised to the 1000-point grid (so3_diffuser.py:301);
+                                   NULL = quantise t on the device */
+  const float* res_mask;        /* [B,N] */
+  const float* fixed_mask;      /* [B,N] */
+  const int32_t* seq_idx;       /* [B,N] 1-based residue index, 0 on padding */
+  const float* sc_ca_t;         /* [B,N,3] self-conditioning CA (Å) */
+  const float* gt_psi;          /* [B,N,2] torsion_angles_sin_cos[..., 2, :] (used where fixed_mask = 1); may be NULL */
+} fd_forward_in;
+
+typedef struct {
+  double* rot_score;            /* [B,N,3] float64, like the reference */
+  double* trans_score;          /* [B,N,3] float64 */
+  float* psi;                   /* [B,N,2] (sin, cos) */
+  float* rigids;                /* [B,N,7] predicted frames, Å */
+  float* atom37;                /* [B,N,37,3]; may be NULL */
+  float* atom14;                /* [B,N,14,3]; may be NULL */
+} fd_forward_out;
+
+int fd_forward(fd_handle h, int B, int N, const fd_forward_in* in, const fd_forward_out* out, void* stream);
+
+/* Debug taps: after fd_set_debug(h,1) every forward keeps copies of named intermediates
+ * ("node_embed","edge_embed","node_<b>","edge_<b>","ipa_feats_<b>","attn_<b>","quat_<b>","trans_<b>").
+ * fd_debug_fetch copies one to a HOST buffer (returns its byte size; dst may be NULL to query). */
+int fd_set_debug(fd_handle h, int on);
+int64_t fd_debug_fetch(fd_handle h, const char* name, void* dst_host, int64_t dst_bytes);
+
+/* ---- SE3Diffuser pieces (data/se3_diffuser.py, so3_diffuser.py, r3_diffuser.py) ------------------------------ */
+/* SO3Diffuser.torch_score (so3_diffuser.py:274-305) over n rotation vectors: vec [n,3] fp32, sigma [n] fp64
+ * (quantised), score_out [n,3] fp64.  Device pointers. */
+int fd_igso3_score(fd_handle h, int64_t n, const float* vec, const double* sigma, double* score_out, void* stream);
+
+/* SO3Diffuser.__init__ cache rows (so3_diffuser.py:151-180) for `nrows` sigma-grid indices: pdf/cdf/score_norms
+ * [nrows,1000] fp64 and score_scaling [nrows].  HOST pointers (any may be NULL).  Computed on the GPU. */
+int fd_igso3_tables_host(fd_handle h, int nrows, const int32_t* sigma_idx, double* pdf, double* cdf,
+                         double* score_norms, double* score_scaling);
+
+/* SE3Diffuser.sample_ref (se3_diffuser.py:216-268): prior frames for n residues.  Either inject the reference's
+ * numpy draws (z_axis [n,3] ~N(0,1), u_angle [n] ~U(0,1), z_trans [n,3] ~N(0,1); fp64 device pointers) or pass NULLs
+ * and a Philox key (seed, first_sample, residues_per_sample).  rigids_out [n,7] fp32 device. */
+int fd_sample_ref(fd_handle h, int64_t n, const double* z_axis, const double* u_angle, const double* z_trans,
+                  uint64_t seed, int64_t first_sample, int residues_per_sample, float* rigids_out, void* stream);
+
+/* SE3Diffuser.reverse (se3_diffuser.py:160-214): one reverse-SDE step for B backbones of N residues.
+ * rot_score/trans_score [B,N,3] fp64, diffuse_mask [B,N] fp32 or NULL, z_rot/z_trans [B,N,3] fp64 N(0,1) draws or
+ * NULL (then Philox(seed, first_sample+b, step, residue)).  t, dt: the reference's python floats.
+ * rigids_io [B,N,7] fp32 is updated in place.  rotmat_out [B,N,3,3] fp32 optional (the reference returns a
+ * rotation-matrix-backed Rigid). */
+int fd_reverse_step(fd_handle h, int B, int N, float* rigids_io, const double* rot_score, const double* trans_score,
+                    const float* diffuse_mask, double t, double dt, int center, double noise_scale,
+                    const double* z_rot, const double* z_trans, uint64_t seed, int64_t first_sample, int step,
+                    float* rotmat_out, void* stream);
+
+/* all_atom.compute_backbone (data/all_atom.py:152-174): rigids [n,7] fp32 (Å) + psi [n,2] -> atom37 [n,37,3],
+ * atom14 [n,14,3] (either may be NULL).  Device pointers. */
+int fd_compute_backbone(fd_handle h, int64_t n, const float* rigids, const float* psi, float* atom37, float* atom14,
+                        void* stream);
+
+/* ---- Experiment.inference_fn (experiments/train_se3_diffusion.py:718-818): the whole reverse loop ------------ */
+typedef struct {
+  int B, N;                 /* backbones on this device, residues */
+  int num_t;                /* denoise steps (500) */
+  double min_t;             /* 0.01 */
+  double noise_scale;       /* 0.1 */
+  int center;               /* 1 */
+  int self_condition;       /* 1 */
+  int aux_traj;             /* 0: only final outputs; 1: also per-step trajectories */
+  uint64_t seed;            /* Philox key when no noise is injected */
+  int64_t first_sample;     /* global index of this device's first backbone (multi-GPU batch sharding) */
+  int use_graph;            /* 1: capture one denoise step as a CUDA graph and replay it */
+} fd_sample_cfg;
+
+typedef struct {
+  /* optional injected noise, HOST fp64; NULL -> Philox on device */
+  const double* z_axis;     /* [B,N,3]   prior rotation axes      (np.random.randn) */
+  const double* u_angle;    /* [B,N]     prior angle quantiles    (np.random.rand) */
+  const double* z_trans0;   /* [B,N,3]   prior translations       (np.random.normal) */
+  const double* z_rot;      /* [num_t-1,B,N,3] per-step rotation noise */
+  const double* z_trans;    /* [num_t-1,B,N,3] per-step translation noise */
+  const float* rigids_init; /* [B,N,7] overrides the prior draw when non-NULL */
+  const float* res_mask;    /* [B,N] or NULL (= ones) */
+  const float* fixed_mask;  /* [B,N] or NULL (= zeros) */
+  const int32_t* seq_idx;   /* [B,N] or NULL (= 1..N) */
+} fd_sample_in;
+
+typedef struct {
+  /* HOST buffers; any may be NULL */
+  float* atom37_final;      /* [B,N,37,3]  = prot_traj[0] */
+  float* rigids_final;      /* [B,N,7] */
+  float* psi_final;         /* [B,N,2] */
+  float* prot_traj;         /* [num_t,B,N,37,3]   (aux_traj) time-reversed like the reference (index 0 = t≈0) */
+  float* rigid_traj;        /* [num_t+1,B,N,7]    (aux_traj) */
+  float* trans_traj;        /* [num_t,B,N,3]      (aux_traj) */
+  float* rigid_0_traj;      /* [num_t,B,N,37,3]   (aux_traj) */
+  double* gpu_ms;           /* device time of the loop (CUDA events), ms */
+  int64_t* kernel_launches; /* kernels launched (or graph-replayed) inside the loop */
+} fd_sample_out;
+
+int fd_sample_host(fd_handle h, const fd_sample_cfg* cfg, const fd_sample_in* in, const fd_sample_out* out);
+
+/* Device-resident variant used by bench.py's `value` leg: inputs already in HBM, final atom37/rigids stay in HBM.
+ * rigids_init_dev [B,N,7] fp32 or NULL.  atom37_dev [B,N,37,3], rigids_dev [B,N,7] (may be NULL). */
+int fd_sample_dev(fd_handle h, const fd_sample_cfg* cfg, const float* rigids_init_dev, float* atom37_dev,
+                  float* rigids_dev, double* gpu_ms, int64_t* kernel_launches);
+
+/* ---- introspection for bench.py ---------------------------------------------------------------------------- */
+/* Times (CUDA events on the handle's stream, ms) of the last forward's stages; names via fd_stage_name. */
+int fd_num_stages(void);
+const char* fd_stage_name(int i);
+int fd_set_stage_timing(fd_handle h, int on);
+int fd_stage_times(fd_handle h, double* ms_out /* [fd_num_stages()] */, int64_t* launches_out);
+int64_t fd_forward_flops(int B, int N, int executed);   /* algorithmic FLOPs of one forward */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FRAMEDIFF_B200_H */

@@ -1,0 +1,266 @@
+"""Host-side driver of the B200 FrameDiff engine: a thin Python layer over the C ABI (include/framediff_b200.h).
+
+PyTorch is used only as the owner of device memory (tensors -> raw pointers) and for streams.  All arithmetic of the
+hot path runs in libframediff_b200.so; there is no CPU or eager-PyTorch fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import ForwardIn, ForwardOut, SampleCfg, SampleIn, SampleOut, check
+
+PREC = {"fp32": 0, "bf16x3": 1, "bf16": 2}
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _np_ptr(a: Optional[np.ndarray]):
+    return None if a is None else C.c_void_p(a.ctypes.data)
+
+
+def param_schema():
+    lib = _lib.load()
+    out = []
+    for i in range(lib.fd_num_params()):
+        nd = lib.fd_param_ndim(i)
+        out.append((lib.fd_param_name(i).decode(), tuple(int(lib.fd_param_dim(i, d)) for d in range(nd))))
+    return out
+
+
+class FrameDiffEngine:
+    """One engine per (process, CUDA device)."""
+
+    def __init__(self, device: int | torch.device | str = 0, precision: str = "fp32"):
+        self.lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise _lib.FrameDiffError("FrameDiffEngine needs a CUDA device (B200); there is no CPU fallback")
+        dev = torch.device(device if not isinstance(device, int) else f"cuda:{device}")
+        if dev.type != "cuda":
+            raise _lib.FrameDiffError(f"FrameDiffEngine needs a CUDA device, got {dev}")
+        self.device = torch.device("cuda", dev.index if dev.index is not None else torch.cuda.current_device())
+        h = C.c_void_p()
+        check(self.lib.fd_create(C.byref(h), self.device.index))
+        self._h = h
+        self.set_precision(precision)
+        self._weights_version = None
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                self.lib.fd_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    # ---- configuration -------------------------------------------------------------------------------------------
+    def set_precision(self, precision: str):
+        check(self.lib.fd_set_precision(self._h, PREC[precision]))
+        self.precision = precision
+
+    def load_weights(self, state: Dict[str, "np.ndarray | torch.Tensor"]):
+        """state: the reference's 282-entry state_dict (a leading 'module.' is stripped)."""
+        state = {(k[7:] if k.startswith("module.") else k): v for k, v in state.items()}
+        schema = param_schema()
+        keep, ptrs = [], (C.c_void_p * len(schema))()
+        for i, (name, shape) in enumerate(schema):
+            if name not in state:
+                raise KeyError(f"missing parameter {name}")
+            v = state[name]
+            a = v.detach().to("cpu", torch.float32).contiguous().numpy() if torch.is_tensor(v) else np.ascontiguousarray(v, dtype=np.float32)
+            if tuple(a.shape) != shape:
+                raise ValueError(f"parameter {name}: shape {tuple(a.shape)} != {shape}")
+            keep.append(a)
+            ptrs[i] = a.ctypes.data
+        check(self.lib.fd_load_weights(self._h, ptrs))
+
+    def set_debug(self, on: bool):
+        check(self.lib.fd_set_debug(self._h, int(on)))
+
+    def debug_fetch(self, name: str, shape, dtype=np.float32) -> np.ndarray:
+        out = np.empty(shape, dtype=dtype)
+        n = self.lib.fd_debug_fetch(self._h, name.encode(), _np_ptr(out), out.nbytes)
+        if n < 0:
+            check(int(n))
+        if n != out.nbytes:
+            raise ValueError(f"tap {name}: {n} bytes, expected {out.nbytes}")
+        return out
+
+    # ---- ScoreNetwork.forward ------------------------------------------------------------------------------------------
+    def forward(self, feats: Dict[str, torch.Tensor], want_atoms: bool = True) -> Dict[str, torch.Tensor]:
+        dev = self.device
+        rig = feats["rigids_t"]
+        B, N = rig.shape[0], rig.shape[1]
+        t_in = torch.as_tensor(feats["t"])
+        t_is_f32 = 0 if t_in.dtype == torch.float64 else 1
+        f32 = lambda x: torch.as_tensor(x).to(dev, torch.float32).contiguous()
+        rigids_t = f32(rig)
+        t64 = t_in.to(dev, torch.float64).contiguous()
+        if bool(((t64 < 0) | (t64 > 1)).any()):
+            raise ValueError(f"Invalid t={t_in}")
+        res_mask, fixed_mask = f32(feats["res_mask"]), f32(feats["fixed_mask"])
+        seq_idx = torch.as_tensor(feats["seq_idx"]).to(dev, torch.int32).contiguous()
+        sc_ca = f32(feats["sc_ca_t"])
+        tors = feats.get("torsion_angles_sin_cos")
+        gt_psi = f32(torch.as_tensor(tors)[..., 2, :]) if tors is not None else None
+        out = {
+            "rot_score": torch.empty(B, N, 3, device=dev, dtype=torch.float64),
+            "trans_score": torch.empty(B, N, 3, device=dev, dtype=torch.float64),
+            "psi": torch.empty(B, N, 2, device=dev, dtype=torch.float32),
+            "rigids": torch.empty(B, N, 7, device=dev, dtype=torch.float32),
+        }
+        if want_atoms:
+            out["atom37"] = torch.empty(B, N, 37, 3, device=dev, dtype=torch.float32)
+            out["atom14"] = torch.empty(B, N, 14, 3, device=dev, dtype=torch.float32)
+        fin = ForwardIn(_ptr(rigids_t), _ptr(t64), t_is_f32, None, _ptr(res_mask), _ptr(fixed_mask), _ptr(seq_idx), _ptr(sc_ca),
+                        _ptr(gt_psi))
+        fout = ForwardOut(_ptr(out["rot_score"]), _ptr(out["trans_score"]), _ptr(out["psi"]), _ptr(out["rigids"]),
+                          _ptr(out.get("atom37")), _ptr(out.get("atom14")))
+        stream = torch.cuda.current_stream(dev)
+        check(self.lib.fd_forward(self._h, B, N, C.byref(fin), C.byref(fout), C.c_void_p(stream.cuda_stream)))
+        # dtype semantics of the reference: rot_score is float64; trans_score follows t; psi follows
+        # the torsion features it is mixed with.
+        if t_is_f32:
+            out["trans_score"] = out["trans_score"].to(torch.float32)
+        if tors is not None and torch.as_tensor(tors).dtype == torch.float64:
+            out["psi"] = out["psi"].to(torch.float64)
+        self._keep = (rigids_t, t64, res_mask, fixed_mask, seq_idx, sc_ca, gt_psi)
+        return out
+
+    # ---- SE3Diffuser pieces ----------------------------------------------------------------------------------------------
+    def igso3_score(self, vec: torch.Tensor, sigma: torch.Tensor) -> torch.Tensor:
+        v = vec.to(self.device, torch.float32).contiguous().reshape(-1, 3)
+        s = sigma.to(self.device, torch.float64).contiguous().reshape(-1)
+        out = torch.empty(v.shape[0], 3, device=self.device, dtype=torch.float64)
+        st = torch.cuda.current_stream(self.device)
+        check(self.lib.fd_igso3_score(self._h, v.shape[0], _ptr(v), _ptr(s), _ptr(out), C.c_void_p(st.cuda_stream)))
+        return out.reshape(vec.shape)
+
+    def igso3_tables(self, sigma_idx):
+        idx = np.ascontiguousarray(sigma_idx, dtype=np.int32).reshape(-1)
+        n = idx.shape[0]
+        pdf, cdf, sn = (np.empty((n, 1000)) for _ in range(3))
+        sc = np.empty(n)
+        check(self.lib.fd_igso3_tables_host(self._h, n, _np_ptr(idx), _np_ptr(pdf), _np_ptr(cdf), _np_ptr(sn), _np_ptr(sc)))
+        return {"pdf": pdf, "cdf": cdf, "score_norms": sn, "score_scaling": sc}
+
+    def sample_ref(self, n: int, z_axis=None, u_angle=None, z_trans=None, seed=0, first_sample=0, per_sample=None):
+        dev = self.device
+        out = torch.empty(n, 7, device=dev, dtype=torch.float32)
+        d = lambda a: None if a is None else torch.as_tensor(np.ascontiguousarray(a, dtype=np.float64)).to(dev)
+        za, ua, zt = d(z_axis), d(u_angle), d(z_trans)
+        st = torch.cuda.current_stream(dev)
+        check(self.lib.fd_sample_ref(self._h, n, _ptr(za), _ptr(ua), _ptr(zt), seed, first_sample, per_sample or n, _ptr(out),
+                                     C.c_void_p(st.cuda_stream)))
+        torch.cuda.current_stream(dev).synchronize()
+        return out
+
+    def reverse_step(self, rigids: torch.Tensor, rot_score, trans_score, t: float, dt: float, diffuse_mask=None, center=True,
+                     noise_scale=1.0, z_rot=None, z_trans=None, seed=0, first_sample=0, step=0, want_rotmat=False):
+        """In-place on a copy: returns (rigids_{t-1} [B,N,7] fp32, rotmat or None)."""
+        dev = self.device
+        B, N = rigids.shape[:2]
+        r = rigids.to(dev, torch.float32).contiguous().clone()
+        d64 = lambda a: None if a is None else torch.as_tensor(a).to(dev, torch.float64).contiguous()
+        rs, ts, zr, zt = d64(rot_score), d64(trans_score), d64(z_rot), d64(z_trans)
+        dm = None if diffuse_mask is None else torch.as_tensor(diffuse_mask).to(dev, torch.float32).contiguous()
+        rm = torch.empty(B, N, 3, 3, device=dev, dtype=torch.float32) if want_rotmat else None
+        st = torch.cuda.current_stream(dev)
+        check(self.lib.fd_reverse_step(self._h, B, N, _ptr(r), _ptr(rs), _ptr(ts), _ptr(dm), float(t), float(dt), int(center),
+                                       float(noise_scale), _ptr(zr), _ptr(zt), seed, first_sample, step, _ptr(rm),
+                                       C.c_void_p(st.cuda_stream)))
+        st.synchronize()
+        return r, rm
+
+    def compute_backbone(self, rigids: torch.Tensor, psi: torch.Tensor):
+        dev = self.device
+        shp = rigids.shape[:-1]
+        r = rigids.to(dev, torch.float32).contiguous().reshape(-1, 7)
+        p = psi.to(dev, torch.float32).contiguous().reshape(-1, 2)
+        n = r.shape[0]
+        a37 = torch.empty(n, 37, 3, device=dev, dtype=torch.float32)
+        a14 = torch.empty(n, 14, 3, device=dev, dtype=torch.float32)
+        st = torch.cuda.current_stream(dev)
+        check(self.lib.fd_compute_backbone(self._h, n, _ptr(r), _ptr(p), _ptr(a37), _ptr(a14), C.c_void_p(st.cuda_stream)))
+        st.synchronize()
+        return a37.reshape(*shp, 37, 3), a14.reshape(*shp, 14, 3)
+
+    # ---- Experiment.inference_fn ---------------------------------------------------------------------------------------------
+    def sample(self, B: int, N: int, num_t: int = 500, min_t: float = 0.01, noise_scale: float = 0.1, center: bool = True,
+               self_condition: bool = True, aux_traj: bool = False, seed: int = 123, first_sample: int = 0,
+               use_graph: bool = True, rigids_init=None, noise: Optional[dict] = None, res_mask=None, fixed_mask=None,
+               seq_idx=None, pinned: bool = True) -> dict:
+        """Whole reverse loop through fd_sample_host: HOST buffers in / out (H2D + D2H inside the call).
+
+        noise: optional dict of injected numpy draws {z_axis,u_angle,z_trans0,z_rot,z_trans} (float64).
+        Returns the reference's inference_fn dict (prot_traj, and rigid_traj/trans_traj/rigid_0_traj/psi_pred when
+        aux_traj) plus 'gpu_ms' and 'kernel_launches'.  Without aux_traj, prot_traj has a single frame (the sample).
+        """
+        cfg = SampleCfg(B, N, num_t, min_t, noise_scale, int(center), int(self_condition), int(aux_traj), seed, first_sample,
+                        int(use_graph))
+        keep = []
+
+        def host(a, dtype):
+            if a is None:
+                return None
+            x = np.ascontiguousarray(a.detach().cpu().numpy() if torch.is_tensor(a) else a, dtype=dtype)
+            keep.append(x)
+            return x
+
+        noise = noise or {}
+        sin = SampleIn(*[_np_ptr(host(noise.get(k), np.float64)) for k in ("z_axis", "u_angle", "z_trans0", "z_rot", "z_trans")],
+                       _np_ptr(host(rigids_init, np.float32)), _np_ptr(host(res_mask, np.float32)),
+                       _np_ptr(host(fixed_mask, np.float32)), _np_ptr(host(seq_idx, np.int32)))
+
+        def out_buf(shape):
+            t = torch.empty(shape, dtype=torch.float32, pin_memory=pinned)
+            keep.append(t)
+            return t
+
+        a37, rig, psi = out_buf((B, N, 37, 3)), out_buf((B, N, 7)), out_buf((B, N, 2))
+        tr = {}
+        if aux_traj:
+            tr = {"prot_traj": out_buf((num_t, B, N, 37, 3)), "rigid_traj": out_buf((num_t + 1, B, N, 7)),
+                  "trans_traj": out_buf((num_t, B, N, 3)), "rigid_0_traj": out_buf((num_t, B, N, 37, 3))}
+        ms, nl = C.c_double(0), C.c_int64(0)
+        sout = SampleOut(_ptr(a37), _ptr(rig), _ptr(psi), _ptr(tr.get("prot_traj")), _ptr(tr.get("rigid_traj")),
+                         _ptr(tr.get("trans_traj")), _ptr(tr.get("rigid_0_traj")), C.pointer(ms), C.pointer(nl))
+        check(self.lib.fd_sample_host(self._h, C.byref(cfg), C.byref(sin), C.byref(sout)))
+        ret = {"gpu_ms": ms.value, "kernel_launches": nl.value, "rigids_final": rig.numpy(), "psi_pred": psi.numpy()[None]}
+        if aux_traj:
+            ret.update({k: v.numpy() for k, v in tr.items()})
+        else:
+            ret["prot_traj"] = a37.numpy()[None]
+        return ret
+
+    def sample_device(self, B: int, N: int, num_t: int = 500, min_t: float = 0.01, noise_scale: float = 0.1, seed: int = 123,
+                      first_sample: int = 0, use_graph: bool = True, rigids_init: Optional[torch.Tensor] = None):
+        """Device-resident loop (bench `value` leg): returns (atom37 cuda tensor, rigids cuda tensor, gpu_ms, launches)."""
+        cfg = SampleCfg(B, N, num_t, min_t, noise_scale, 1, 1, 0, seed, first_sample, int(use_graph))
+        a37 = torch.empty(B, N, 37, 3, device=self.device, dtype=torch.float32)
+        rig = torch.empty(B, N, 7, device=self.device, dtype=torch.float32)
+        ms, nl = C.c_double(0), C.c_int64(0)
+        ri = None if rigids_init is None else rigids_init.to(self.device, torch.float32).contiguous()
+        torch.cuda.synchronize(self.device)
+        check(self.lib.fd_sample_dev(self._h, C.byref(cfg), _ptr(ri), _ptr(a37), _ptr(rig), C.byref(ms), C.byref(nl)))
+        return a37, rig, ms.value, nl.value
+
+    # ---- introspection -------------------------------------------------------------------------------------------------------
+    def stage_timing(self, on: bool):
+        check(self.lib.fd_set_stage_timing(self._h, int(on)))
+
+    def stage_times(self):
+        n = self.lib.fd_num_stages()
+        ms = (C.c_double * n)()
+        nl = (C.c_int64 * n)()
+        check(self.lib.fd_stage_times(self._h, ms, nl))
+        return {self.lib.fd_stage_name(i).decode(): (ms[i], nl[i]) for i in range(n)}
+
+    def forward_flops(self, B, N, executed=True):
+        return int(self.lib.fd_forward_flops(B, N, int(executed)))
