@@ -200,9 +200,11 @@ extern "C" int fd_create(fd_handle* out, int device) {
     CKI(build_igso3_rows(h, 1, &idx, nullptr, cdf.data(), nullptr, nullptr));
     CK(cudaMemcpy(h->d_cdf_t1, cdf.data(), SO3_NOMEGA * sizeof(double), cudaMemcpyHostToDevice));
   }
-  CK(cudaFuncSetAttribute(ipa_edge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+  CK(cudaFuncSetAttribute(ipa_edge_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+  CK(cudaFuncSetAttribute(ipa_edge_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+  CK(cudaFuncSetAttribute(ipa_edge_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
   CK(cudaFuncSetAttribute(reverse_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-  CKI(tc_init(h->sm_count));
+  if (tc_init(h->sm_count)) return fail(FD_ECUDA, "tensor-core path initialisation failed (cuTensorMapEncodeTiled entry point / smem attribute)");
   *out = h;
   return FD_OK;
 }
@@ -400,7 +402,7 @@ extern "C" int fd_load_weights(fd_handle h, const float* const* P) {
   rel_table_kernel<<<2 * REL_DMAX + 1, 128, 0, h->stream>>>(W.ee_w0r, W.ee_T);
   CK(cudaGetLastError());
   // bf16 hi/lo images for the tensor-core edge kernels
-  CKI(tc_pack_weights(h->tcw, M, h->stream));
+  if (tc_pack_weights(h->tcw, M, h->stream)) return fail(FD_ECUDA, "packing bf16 weight planes failed: %s", cudaGetErrorString(cudaGetLastError()));
   CK(cudaStreamSynchronize(h->stream));
   h->weights_loaded = true;
   return FD_OK;
@@ -443,7 +445,7 @@ static int ensure_ws(fd_context* h, int B, int N) {
   w.bytes = total;
   char* p = w.base;
   for (auto& it : items) { *it.p = reinterpret_cast<float*>(p); p += al256(it.n * sizeof(float)); }
-  if (tc) tc_bind_workspace(w.tc, p, B, N);
+  if (tc && tc_bind_workspace(w.tc, p, B, N)) return fail(FD_ECUDA, "cuTensorMapEncodeTiled failed for the edge-tensor planes");
   return FD_OK;
 }
 
@@ -543,11 +545,15 @@ static int forward_impl(fd_context* h, int B, int N, const float* rigids_t, cons
   edge_l0_node_terms_kernel<<<(unsigned)((R * 256 + 255) / 256), 256, 0, st>>>(w.temb, fixed_mask, W.ee_w0a, W.ee_w0c, W.ee_b0, w.AC, R, N);
   f.check("edge_l0_node_terms");
   if (tc) {
-    if (!f.err) f.err = tc_edge_embed(h->tcw, w.tc, h->precision, w.AC, W.ee_T, W.ee_D, W.ee_w0r, seq_idx, sc_ca, res_mask, B, N, st, &h->launches);
+    if (!f.err) {
+      const int rc = tc_edge_embed(h->tcw, w.tc, h->precision, w.AC, W.ee_T, W.ee_D, W.ee_w0r, seq_idx, sc_ca, res_mask, W.ee2.b, W.ee4.b,
+                                   W.ee_ln.g, W.ee_ln.b, B, N, st, &h->launches);
+      if (rc) f.err = fail(rc == -1 ? FD_EINVAL : FD_ECUDA, "tensor-core edge embedder launch failed (%d): %s", rc, cudaGetErrorString(cudaGetLastError()));
+    }
   } else {
     for (long long r0 = 0; r0 < w.edges && !f.err; r0 += w.chunk) {
       const long long m = (w.edges - r0 < w.chunk) ? w.edges - r0 : w.chunk;
-      edge_embed_l0_kernel<<<(unsigned)((m + 7) / 8), 256, 0, st>>>(w.AC, W.ee_T, W.ee_D, W.ee_w0r, seq_idx, sc_ca, w.h1, r0, m, N);
+      edge_embed_l0_kernel<0><<<(unsigned)((m + 7) / 8), 256, 0, st>>>(w.AC, W.ee_T, W.ee_D, W.ee_w0r, seq_idx, sc_ca, w.h1, nullptr, nullptr, r0, m, N);
       f.check("edge_embed_l0");
       f.linear(w.h1, 128, W.ee2, 128, 128, w.h2, 128, m, true);
       f.linear(w.h2, 128, W.ee4, 128, 128, w.ychunk, 128, m);
@@ -560,7 +566,7 @@ static int forward_impl(fd_context* h, int B, int N, const float* rigids_t, cons
   }
   lc.end();
   if (h->debug && !f.err) {
-    if (tc) tc_export_z(w.tc, w.z, B, N, st);
+    if (tc) tc_export_z(w.tc, w.z, h->precision, st);
     snap(h, "edge_embed", w.z, (size_t)w.edges * C_Z * 4, st);
   }
 
@@ -590,9 +596,11 @@ static int forward_impl(fd_context* h, int B, int N, const float* rigids_t, cons
     if (!f.err) {
       const size_t smem = (size_t)(H * Np + H * PQ * 3 + 2 * H * C_Z) * sizeof(float);
       if (tc) {
-        f.err = tc_ipa_edge(w.tc, w.L, w.qp, w.kp, res_mask, X.Wb, X.bb, X.gamma, X.WdT, X.bd, w.feats, B, N, Np, h->precision, st, &h->launches);
+        if (tc_ipa_edge(w.tc, w.L, w.qp, w.kp, res_mask, X.Wb, X.bb, X.gamma, X.WdT, X.bd, w.feats, B, N, Np, h->precision, st, &h->launches))
+          f.err = fail(FD_ECUDA, "ipa_edge (planes) launch failed: %s", cudaGetErrorString(cudaGetLastError()));
       } else {
-        ipa_edge_kernel<<<dim3(N, B), 256, smem, st>>>(w.z, w.L, w.qp, w.kp, res_mask, X.Wb, X.bb, X.gamma, X.WdT, X.bd, w.feats, N, Np);
+        ZRef zr; zr.f32 = w.z;
+        ipa_edge_kernel<0><<<dim3(N, B), 256, smem, st>>>(zr, w.L, w.qp, w.kp, res_mask, X.Wb, X.bb, X.gamma, X.WdT, X.bd, w.feats, N, Np);
         f.check("ipa_edge");
       }
     }
@@ -672,7 +680,10 @@ static int forward_impl(fd_context* h, int B, int N, const float* rigids_t, cons
       f.linear(w.node, C_S, X.et_init, C_S, C_Z, w.nb, C_Z, R);
       f.linear(w.nb, C_Z, X.et_node, C_Z, ET_NODE, w.pquv, ET_NODE, R);
       if (tc) {
-        if (!f.err) f.err = tc_edge_transition(h->tcw, w.tc, b, h->precision, w.pquv, X.et_w2.b, X.et_ln.g, X.et_ln.b, res_mask, B, N, st, &h->launches);
+        if (!f.err) {
+          const int rc = tc_edge_transition(h->tcw, w.tc, b, h->precision, w.pquv, X.et_w2.b, X.et_ln.g, X.et_ln.b, res_mask, B, N, st, &h->launches);
+          if (rc) f.err = fail(rc == -1 ? FD_EINVAL : FD_ECUDA, "tensor-core edge transition launch failed (%d): %s", rc, cudaGetErrorString(cudaGetLastError()));
+        }
       } else {
         for (long long r0 = 0; r0 < w.edges && !f.err; r0 += w.chunk) {
           const long long m = (w.edges - r0 < w.chunk) ? w.edges - r0 : w.chunk;
@@ -698,7 +709,7 @@ static int forward_impl(fd_context* h, int B, int N, const float* rigids_t, cons
       }
       lc.end();
       if (h->debug && !f.err) {
-        if (tc) tc_export_z(w.tc, w.z, B, N, st);
+        if (tc) tc_export_z(w.tc, w.z, h->precision, st);
         snap(h, "edge_" + sb, w.z, (size_t)w.edges * C_Z * 4, st);
       }
     }

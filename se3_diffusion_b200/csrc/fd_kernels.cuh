@@ -1,6 +1,7 @@
 // CUDA-core kernels of the FrameDiff forward (everything that is not a big GEMM chain) and of the SE(3) diffuser.
 // Each kernel cites the reference lines whose arithmetic it implements (paths relative to /root/reference).
 #pragma once
+#include <cuda_bf16.h>
 #include "fd_common.cuh"
 #include "fd_constants.h"
 
@@ -10,6 +11,40 @@ __constant__ float c_time_freq[16];
 __constant__ float c_idx_den[16];
 __constant__ float c_dgram_lower[NBINS];
 __constant__ float c_pi_f32;
+
+// Edge tensor storage.  fp32 mode: z [E,128] fp32.  Tensor-core modes: bf16 "hi" plane (+ "lo" plane = bf16(z - hi) in
+// the 3-term split mode), each [E,128]; z = hi (+ lo).
+struct ZRef {
+  const float* f32 = nullptr;
+  const __nv_bfloat16* hi = nullptr;
+  const __nv_bfloat16* lo = nullptr;
+};
+template <int ZMODE>   // 0 fp32, 1 hi, 2 hi+lo
+__device__ __forceinline__ float4 z_load4(const ZRef& z, long long elem /* multiple of 4 */) {
+  if (ZMODE == 0) return *reinterpret_cast<const float4*>(z.f32 + elem);
+  const uint2 h = *reinterpret_cast<const uint2*>(z.hi + elem);
+  float4 r;
+  r.x = __uint_as_float(h.x << 16); r.y = __uint_as_float(h.x & 0xffff0000u);
+  r.z = __uint_as_float(h.y << 16); r.w = __uint_as_float(h.y & 0xffff0000u);
+  if (ZMODE == 2) {
+    const uint2 l = *reinterpret_cast<const uint2*>(z.lo + elem);
+    r.x += __uint_as_float(l.x << 16); r.y += __uint_as_float(l.x & 0xffff0000u);
+    r.z += __uint_as_float(l.y << 16); r.w += __uint_as_float(l.y & 0xffff0000u);
+  }
+  return r;
+}
+template <int ZMODE>
+__device__ __forceinline__ float z_load1(const ZRef& z, long long elem) {
+  if (ZMODE == 0) return z.f32[elem];
+  float r = __bfloat162float(z.hi[elem]);
+  if (ZMODE == 2) r += __bfloat162float(z.lo[elem]);
+  return r;
+}
+// fp32 -> (hi, lo) bf16 split, round-to-nearest both
+__device__ __forceinline__ void split_bf16(float v, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+  hi = __float2bfloat16_rn(v);
+  lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+}
 
 // ----------------------------------------------------------------------------------------------------------------
 // LayerNorm over rows of width C (128 / 256 / 320), one warp per row.  torch.nn.LayerNorm, eps 1e-5, biased var.
@@ -196,10 +231,12 @@ __device__ __forceinline__ int dgram_bin(float d) {
 
 // Edge embedder layer 0 for a chunk of edge rows: h[row][c] = relu(A_i + C_j + T[i-j] + D[bin]).  One warp per row,
 // one float4 of channels per lane.  `split` != 0 additionally emits the bf16 hi/lo planes for the tensor-core path.
+template <int OMODE>   // 0: fp32 h; 1: bf16 hi plane; 2: hi + lo planes
 __global__ void __launch_bounds__(256) edge_embed_l0_kernel(
     const float* __restrict__ AC, const float* __restrict__ T, const float* __restrict__ D /* [NBINS+1][128] */,
     const float* __restrict__ w0r, const int* __restrict__ seq_idx, const float* __restrict__ sc_ca,
-    float* __restrict__ h, long long row_offset, long long rows, int N) {
+    float* __restrict__ h, __nv_bfloat16* __restrict__ h_hi, __nv_bfloat16* __restrict__ h_lo, long long row_offset,
+    long long rows, int N) {
   const int lane = threadIdx.x & 31;
   const long long r = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (r >= rows) return;
@@ -235,7 +272,14 @@ __global__ void __launch_bounds__(256) edge_embed_l0_kernel(
   o.y = fmaxf(((a.y + c.y) + tr.y) + dg.y, 0.f);
   o.z = fmaxf(((a.z + c.z) + tr.z) + dg.z, 0.f);
   o.w = fmaxf(((a.w + c.w) + tr.w) + dg.w, 0.f);
-  reinterpret_cast<float4*>(h + r * 128)[lane] = o;
+  if (OMODE == 0) {
+    reinterpret_cast<float4*>(h + r * 128)[lane] = o;
+  } else {
+    __nv_bfloat16 hi[4], lo[4];
+    split_bf16(o.x, hi[0], lo[0]); split_bf16(o.y, hi[1], lo[1]); split_bf16(o.z, hi[2], lo[2]); split_bf16(o.w, hi[3], lo[3]);
+    *reinterpret_cast<uint2*>(h_hi + r * 128 + lane * 4) = *reinterpret_cast<const uint2*>(hi);
+    if (OMODE == 2) *reinterpret_cast<uint2*>(h_lo + r * 128 + lane * 4) = *reinterpret_cast<const uint2*>(lo);
+  }
 }
 
 // ----------------------------------------------------------------------------------------------------------------
@@ -282,8 +326,9 @@ __global__ void ipa_points_kernel(const float* __restrict__ proj, const float* _
 //   o_pair[h] = Wd·(Σ_j a[h][j] z_ij) + bd    -> feats[:, 2432 + h*32 + d]   (Σ_j a = 1, so bd factors out)
 // z row (N×128 fp32) is streamed twice; the second pass hits L2.
 // ----------------------------------------------------------------------------------------------------------------
+template <int ZMODE>
 __global__ void __launch_bounds__(256) ipa_edge_kernel(
-    const float* __restrict__ z, float* __restrict__ L, const float* __restrict__ qp, const float* __restrict__ kp,
+    const ZRef z, float* __restrict__ L, const float* __restrict__ qp, const float* __restrict__ kp,
     const float* __restrict__ res_mask, const float* __restrict__ Wb, const float* __restrict__ bb,
     const float* __restrict__ gamma, const float* __restrict__ WdT, const float* __restrict__ bd,
     float* __restrict__ feats, int N, int Np) {
@@ -309,7 +354,7 @@ __global__ void __launch_bounds__(256) ipa_edge_kernel(
   }
   __syncthreads();
 
-  const float* zrow = z + rowi * N * C_Z;
+  const long long zrow = rowi * N * C_Z;   // element offset of z[b,i,0,0]
   const int myh = lane >> 2;
   const float my_bb = bb[myh], my_g = gamma[myh];
   float q6[6];
@@ -317,7 +362,7 @@ __global__ void __launch_bounds__(256) ipa_edge_kernel(
   for (int e = 0; e < 6; ++e) q6[e] = qs[lane * 6 + e];
   const float k13 = 0.57735026918962576f;  // sqrt(1/3)
   for (int j = warp; j < N; j += 8) {
-    const float4 zv = reinterpret_cast<const float4*>(zrow + (long long)j * C_Z)[lane];
+    const float4 zv = z_load4<ZMODE>(z, zrow + (long long)j * C_Z + lane * 4);
     const float2* kpj = reinterpret_cast<const float2*>(kp + ((long long)b * N + j) * (H * PQ * 3)) + lane * 3;
     const float2 k0 = kpj[0], k1 = kpj[1], k2 = kpj[2];
     float d2;
@@ -400,7 +445,7 @@ __global__ void __launch_bounds__(256) ipa_edge_kernel(
     for (int j0 = half * 4; j0 < N; j0 += 8) {
       float zc[4];
 #pragma unroll
-      for (int jj = 0; jj < 4; ++jj) zc[jj] = j0 + jj < N ? zrow[(long long)(j0 + jj) * C_Z + c] : 0.f;
+      for (int jj = 0; jj < 4; ++jj) zc[jj] = j0 + jj < N ? z_load1<ZMODE>(z, zrow + (long long)(j0 + jj) * C_Z + c) : 0.f;
 #pragma unroll
       for (int h = 0; h < H; ++h) {
         const float4 a4 = *reinterpret_cast<const float4*>(lg + h * Np + j0);
