@@ -1132,6 +1132,17 @@ extern "C" int fd_sample_dev(fd_handle h, const fd_sample_cfg* cfg, const float*
 // ------------------------------------------------------------------------------------------------------------------
 // introspection
 // ------------------------------------------------------------------------------------------------------------------
+// Developer aid (not in the public header): cycle counters of the fused EdgeTransition kernel's roles (CTA 0, last launch).
+extern "C" int fd_debug_tc_profile(fd_handle h, int on, long long* out32) {
+  if (!h) return FD_EINVAL;
+  cudaSetDevice(h->device);
+  cudaDeviceSynchronize();
+  if (on && !g_tc_prof) { cudaMalloc(&g_tc_prof, 32 * sizeof(long long)); cudaMemset(g_tc_prof, 0, 32 * sizeof(long long)); }
+  if (out32 && g_tc_prof) cudaMemcpy(out32, g_tc_prof, 32 * sizeof(long long), cudaMemcpyDeviceToHost);
+  if (!on && g_tc_prof) { cudaFree(g_tc_prof); g_tc_prof = nullptr; }
+  return FD_OK;
+}
+
 extern "C" int fd_num_stages(void) { return ST_COUNT; }
 extern "C" const char* fd_stage_name(int i) { return (i < 0 || i >= ST_COUNT) ? nullptr : kStageNames[i]; }
 extern "C" int fd_set_stage_timing(fd_handle h, int on) {

@@ -20,6 +20,7 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
+#include <stdlib.h>
 #include <map>
 #include <string>
 #include <vector>
@@ -65,6 +66,20 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
+// (v0, v1) -> packed bf16x2 hi and lo words (hi = rn(v), lo = rn(v - hi)); low half = first element
+__device__ __forceinline__ void split2_bf16(float v0, float v1, uint32_t& hi, uint32_t& lo) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  const float r0 = v0 - __uint_as_float(hi << 16), r1 = v1 - __uint_as_float(hi & 0xffff0000u);
+  const __nv_bfloat162 l = __floats2bfloat162_rn(r0, r1);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+// one elected lane of a converged warp (CUTLASS elect_one_sync): operands stay warp-uniform, only the issue is predicated
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred)::"memory");
+  return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
@@ -90,6 +105,34 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
       : "r"(taddr)
       : "memory");
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ void tc_commit_elect(uint32_t bar) {
+  if (elect_one()) tc_commit(bar);
+  __syncwarp();
+}
+// One k-step (K = 16) of the split product into accumulator d:  hi·hi (+ hi·lo + lo·hi when three_pass).
+// acc0 = 0 makes the first MMA overwrite d.  Descriptors are 64-bit values; advancing 32 B along K adds 2.
+__device__ __forceinline__ void umma_kstep(uint32_t d, uint64_t aH, uint64_t aL, uint64_t bH, uint64_t bL, uint32_t idesc, uint32_t acc0,
+                                           bool three_pass) {
+  if (three_pass) {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "setp.eq.b32 q, 0, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %3, %5, p;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %4, %5, q;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %2, %3, %5, q;\n\t}" ::"r"(d),
+        "l"(aH), "l"(aL), "l"(bH), "l"(bL), "r"(idesc), "r"(acc0)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d),
+        "l"(aH), "l"(bH), "r"(idesc), "r"(acc0)
+        : "memory");
+  }
 }
 
 // K-major, 128B-swizzled smem operand descriptor (rows of 64 bf16 = 128 B, 8-row swizzle atoms of 1024 B)
@@ -151,7 +194,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mA0h, const __grid_constant__
   const uint32_t tmem_empty = tmem_full + 8u;
   const uint32_t tmem_ptr_addr = tmem_empty + 8u;
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int KB = p.KB0 + p.KB1;
   const int NCH = p.N / TC_NC;
   const uint32_t stage_bytes = (uint32_t)p.planes * TC_PLANE_BYTES;
@@ -178,27 +221,33 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mA0h, const __grid_constant__
 
   if (warp == 0) {
     // ================================ TMA producer ================================
-    if (lane == 0) {
-      uint32_t ia = 0, ib = 0;   // running stage counters
+    {
+      uint32_t ia = 0, ib = 0;   // running stage counters (whole warp runs the loop; one elected lane issues)
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         const int m0 = tile * TC_BM;
         for (int kb = 0; kb < KB; ++kb) {
           const uint32_t sa = ia % TC_SA, pa = (ia / TC_SA) & 1u;
           mbar_wait(a_empty(sa), pa ^ 1u);
-          mbar_expect_tx(a_full(sa), stage_bytes);
           const bool first = kb < p.KB0;
           const int ka = (first ? kb : kb - p.KB0) * TC_BK;
           const uint32_t dstA = a_ring + sa * 2 * TC_PLANE_BYTES;
-          tma_load_2d(dstA, first ? &mA0h : &mA1h, a_full(sa), ka, m0);
-          if (p.planes == 2) tma_load_2d(dstA + TC_PLANE_BYTES, first ? &mA0l : &mA1l, a_full(sa), ka, m0);
+          if (elect_one()) {
+            mbar_expect_tx(a_full(sa), stage_bytes);
+            tma_load_2d(dstA, first ? &mA0h : &mA1h, a_full(sa), ka, m0);
+            if (p.planes == 2) tma_load_2d(dstA + TC_PLANE_BYTES, first ? &mA0l : &mA1l, a_full(sa), ka, m0);
+          }
+          __syncwarp();
           ++ia;
           for (int c = 0; c < NCH; ++c) {
             const uint32_t sb = ib % TC_SB, pb = (ib / TC_SB) & 1u;
             mbar_wait(b_empty(sb), pb ^ 1u);
-            mbar_expect_tx(b_full(sb), stage_bytes);
             const uint32_t dstB = b_ring + sb * 2 * TC_PLANE_BYTES;
-            tma_load_2d(dstB, &mBh, b_full(sb), kb * TC_BK, c * TC_NC);
-            if (p.planes == 2) tma_load_2d(dstB + TC_PLANE_BYTES, &mBl, b_full(sb), kb * TC_BK, c * TC_NC);
+            if (elect_one()) {
+              mbar_expect_tx(b_full(sb), stage_bytes);
+              tma_load_2d(dstB, &mBh, b_full(sb), kb * TC_BK, c * TC_NC);
+              if (p.planes == 2) tma_load_2d(dstB + TC_PLANE_BYTES, &mBl, b_full(sb), kb * TC_BK, c * TC_NC);
+            }
+            __syncwarp();
             ++ib;
           }
         }
@@ -206,7 +255,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mA0h, const __grid_constant__
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ================================
-    if (lane == 0) {
+    {
       const uint32_t idesc = make_idesc_bf16(TC_BM, TC_NC);
       uint32_t ia = 0, ib = 0, it = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
@@ -223,23 +272,20 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mA0h, const __grid_constant__
             tc_fence_after();
             const uint32_t bH = b_ring + sb * 2 * TC_PLANE_BYTES, bL = bH + TC_PLANE_BYTES;
             const uint32_t d = tmem_base + (uint32_t)(c * TC_NC);
+            const uint64_t dAH = make_sw128_desc(aH), dAL = make_sw128_desc(aL), dBH = make_sw128_desc(bH), dBL = make_sw128_desc(bL);
+            if (elect_one()) {
 #pragma unroll
-            for (int ks = 0; ks < TC_BK / 16; ++ks) {
-              const uint32_t ko = ks * 32;   // 16 bf16 = 32 bytes along K inside the swizzle atom
-              const uint32_t acc0 = (kb > 0 || ks > 0) ? 1u : 0u;
-              umma_bf16(d, make_sw128_desc(aH + ko), make_sw128_desc(bH + ko), idesc, acc0);
-              if (p.planes == 2) {
-                umma_bf16(d, make_sw128_desc(aH + ko), make_sw128_desc(bL + ko), idesc, 1u);
-                umma_bf16(d, make_sw128_desc(aL + ko), make_sw128_desc(bH + ko), idesc, 1u);
-              }
+              for (int ks = 0; ks < TC_BK / 16; ++ks)   // 16 bf16 = 32 bytes along K inside the swizzle atom: descriptor += 2
+                umma_kstep(d, dAH + 2u * ks, dAL + 2u * ks, dBH + 2u * ks, dBL + 2u * ks, idesc, (kb > 0 || ks > 0) ? 1u : 0u, p.planes == 2);
+              tc_commit(b_empty(sb));     // frees this weight stage once the MMAs above retire
             }
-            tc_commit(b_empty(sb));     // frees this weight stage once the MMAs above retire
+            __syncwarp();
             ++ib;
           }
-          tc_commit(a_empty(sa));
+          tc_commit_elect(a_empty(sa));
           ++ia;
         }
-        tc_commit(tmem_full);           // accumulators complete -> epilogue
+        tc_commit_elect(tmem_full);           // accumulators complete -> epilogue
       }
     }
   } else {
@@ -350,6 +396,458 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mA0h, const __grid_constant__
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// Fused EdgeTransition kernel (model/ipa_pytorch.py:218-233): one launch per layer, z read once and written once.
+//
+//   per 128-edge tile:  h1 = relu(z·W1z^T + P_i + Q_j)   6 chunks of 64 hidden units: G1_c (SS MMA, A = z tile in smem) -> TMEM T1[c&1]
+//                                                          -> epilogue -> bf16 hi/lo written back IN PLACE into T1[c&1]
+//                       H2 += h1_c · W2[:, 64c:64c+64]^T  G2_c: TS MMA, A = T1[c&1] (TMEM), K = 64, N = 384 -> TMEM H2
+//                       h2 = relu(H2 + b2)                6 chunks of 64 -> bf16 hi/lo in place over H2's own columns
+//                       Y  = z·Wfz^T (G3z, SS) + sum_c h2_c · Wf[:, 64c:64c+64]^T (G3_c, TS)      -> TMEM Y (reuses T1)
+//                       z' = LayerNorm(Y + U_i + V_j) · m_i m_j  -> bf16 hi/lo planes (in place: tiles are row-disjoint)
+//   TMEM: [0,64) T1a  [64,128) T1b  [128,512) H2 ; Y = [0,128).  A-operand image of a 64-wide chunk inside its 64 fp32 columns:
+//         columns [0,32) = hi (two bf16 per 32-bit column, K ascending), columns [32,64) = lo.
+//   Activations never touch shared memory: the MMAs of the two big GEMMs read A from TMEM, so shared-memory bandwidth only
+//   carries the weight blocks (an SS 128x128x16 MMA needs 128 B/clk of smem — the whole budget — a TS one 64 B/clk).
+//   smem: z tile 64 KB (TMA)  |  weight ring 160 KB (TMA; every weight block streams from L2 once per tile)  |  mbarriers.
+//   warps: 0 = TMA producer, 1 = MMA issuer (+TMEM alloc), 2..9 = epilogue: two groups of four warps (one per TMEM lane quadrant);
+//          group g converts the chunks of parity g, 64 columns per thread-row per step.
+//   Ordering between MMAs that reuse TMEM columns (G2_c reads T1[x] then G1_{c+2} overwrites it; G3_5 reads H2 then the next
+//   tile's G2_0 overwrites it) relies on tcgen05.mma executing in issue order.
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]),
+      "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]),
+               "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+        "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// TS k-step: A (bf16, K = 16 -> 8 TMEM columns) from tensor memory, B from shared memory
+__device__ __forceinline__ void umma_kstep_ts(uint32_t d, uint32_t aH, uint32_t aL, uint64_t bH, uint64_t bL, uint32_t idesc, uint32_t acc0,
+                                              bool three_pass) {
+  if (three_pass) {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "setp.eq.b32 q, 0, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %3, %5, p;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %4, %5, q;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%2], %3, %5, q;\n\t}" ::"r"(d),
+        "r"(aH), "r"(aL), "l"(bH), "l"(bL), "r"(idesc), "r"(acc0)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d),
+        "r"(aH), "l"(bH), "r"(idesc), "r"(acc0)
+        : "memory");
+  }
+}
+
+// Weight-ring helpers as force-inlined members (warp-uniform: the whole warp runs them, one elected lane issues)
+struct FuRing {
+  uint32_t ringb, bar0, slot_bytes, S, planes;
+  uint32_t iw;
+  long long c_wait; bool prof_on;
+  __device__ __forceinline__ uint32_t slot(uint32_t s, int pl) const { return ringb + s * slot_bytes + (uint32_t)pl * TC_PLANE_BYTES; }
+  __device__ __forceinline__ uint32_t full(uint32_t s) const { return bar0 + 8u * s; }
+  __device__ __forceinline__ uint32_t empty(uint32_t s) const { return bar0 + 8u * (10 + s); }
+  // producer: wait for a free slot, arm it, issue the TMA loads of one weight block
+  __device__ __forceinline__ void load(const CUtensorMap* mh, const CUtensorMap* ml, int k, int n, uint32_t bytes_per_plane) {
+    const uint32_t s = iw % S, ph = (iw / S) & 1u;
+    if (prof_on) { const long long t0 = clock64(); mbar_wait(empty(s), ph ^ 1u); c_wait += clock64() - t0; } else mbar_wait(empty(s), ph ^ 1u);
+    if (elect_one()) {
+      mbar_expect_tx(full(s), planes * bytes_per_plane);
+      tma_load_2d(slot(s, 0), mh, full(s), k, n);
+      if (planes == 2) tma_load_2d(slot(s, 1), ml, full(s), k, n);
+    }
+    __syncwarp();
+    ++iw;
+  }
+  __device__ __forceinline__ uint32_t acquire() {
+    const uint32_t s = iw % S, ph = (iw / S) & 1u;
+    if (prof_on) { const long long t0 = clock64(); mbar_wait(full(s), ph); c_wait += clock64() - t0; } else mbar_wait(full(s), ph);
+    tc_fence_after();
+    return s;
+  }
+  // MMA issuer, SS: one weight block (K = 64) against A planes in shared memory
+  __device__ __forceinline__ void mma_ss(uint32_t aH, uint32_t aL, uint32_t d, uint32_t idesc, bool zero_first) {
+    const uint32_t s = acquire();
+    const uint64_t dAH = make_sw128_desc(aH), dAL = make_sw128_desc(aL);
+    const uint64_t dBH = make_sw128_desc(slot(s, 0)), dBL = make_sw128_desc(slot(s, 1));
+    if (elect_one()) {
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks)
+        umma_kstep(d, dAH + 2u * ks, dAL + 2u * ks, dBH + 2u * ks, dBL + 2u * ks, idesc, (zero_first && ks == 0) ? 0u : 1u, planes == 2);
+      tc_commit(empty(s));
+    }
+    __syncwarp();
+    ++iw;
+  }
+  // MMA issuer, TS: A chunk image in tensor memory (hi at a, lo at a + 32 columns)
+  __device__ __forceinline__ void mma_ts(uint32_t a, uint32_t d, uint32_t idesc, bool zero_first) {
+    const uint32_t s = acquire();
+    const uint64_t dBH = make_sw128_desc(slot(s, 0)), dBL = make_sw128_desc(slot(s, 1));
+    if (elect_one()) {
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks)
+        umma_kstep_ts(d, a + 8u * ks, a + 32u + 8u * ks, dBH + 2u * ks, dBL + 2u * ks, idesc, (zero_first && ks == 0) ? 0u : 1u, planes == 2);
+      tc_commit(empty(s));
+    }
+    __syncwarp();
+    ++iw;
+  }
+};
+
+constexpr int FU_THREADS = 320;   // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two groups of four)
+constexpr int FU_RING_BYTES = 160 * 1024;
+constexpr size_t FU_SMEM_BYTES = 64 * 1024 + FU_RING_BYTES + 512 + 2048;   // dynamic smem starts 1024-aligned (no static smem here)
+
+struct FusedParams {
+  int E, planes, nres, num_tiles;
+  const float* pquv;        // [B*nres, 1024] = P | Q | U | V node terms
+  const float* b2; const float* ln_g; const float* ln_b; const float* res_mask;
+  __nv_bfloat16* out_hi; __nv_bfloat16* out_lo;
+  long long* prof;          // optional [32] cycle counters written by CTA 0 (developer aid)
+  int dbg_noq;              // developer experiment: skip the node-term loads (results wrong; isolates their cost)
+};
+
+#define FU_PROF(ctr, stmt)                               \
+  do {                                                   \
+    if (prof_on) { const long long _t0 = clock64(); stmt; ctr += clock64() - _t0; } else { stmt; } \
+  } while (0)
+
+__global__ void __launch_bounds__(FU_THREADS, 1)
+tc_edge_fused_kernel(const __grid_constant__ CUtensorMap mZh, const __grid_constant__ CUtensorMap mZl,
+                     const __grid_constant__ CUtensorMap mW1h, const __grid_constant__ CUtensorMap mW1l,
+                     const __grid_constant__ CUtensorMap mW2h, const __grid_constant__ CUtensorMap mW2l,
+                     const __grid_constant__ CUtensorMap mWfh, const __grid_constant__ CUtensorMap mWfl, const FusedParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  constexpr uint32_t PL = TC_PLANE_BYTES;   // 16 KB
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t zb = base;                              // z(kb, plane) = zb + (kb*2 + plane)*PL
+  const uint32_t ringb = zb + 4 * PL;
+  const uint32_t bar0 = ringb + FU_RING_BYTES;
+  const int S = p.planes == 2 ? 5 : 10;
+  const uint32_t slot_bytes = (uint32_t)p.planes * PL;
+  auto zbuf = [&](int kb, int pl) { return zb + (uint32_t)(kb * 2 + pl) * PL; };
+  // barriers: ring full[10] (slots 0..9), ring empty[10] (10..19), then the named ones
+  const uint32_t z_full = bar0 + 8u * 20, z_empty = bar0 + 8u * 21;
+  auto t1_full = [&](int x) { return bar0 + 8u * (22 + x); };
+  auto a_full = [&](int x) { return bar0 + 8u * (24 + x); };
+  const uint32_t h2_full = bar0 + 8u * 26, y_full = bar0 + 8u * 27, y_empty = bar0 + 8u * 28;
+  auto a2_full = [&](int c) { return bar0 + 8u * (29 + c); };      // one per h2 chunk (no back-pressure on epi2: avoid 2-phase run-ahead)
+  const uint32_t tmem_ptr_addr = bar0 + 8u * 35;
+  const uint32_t stats = bar0 + 512u;     // LayerNorm partial statistics [2][128 rows][2] fp32 = 2 KB
+
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // warp-uniform by construction
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < 20; ++s) mbar_init(bar0 + 8u * s, 1);
+    mbar_init(z_full, 1); mbar_init(z_empty, 1);
+    for (int x = 0; x < 2; ++x) { mbar_init(t1_full(x), 1); mbar_init(a_full(x), 4); }
+    for (int c = 0; c < 6; ++c) mbar_init(a2_full(c), 4);
+    mbar_init(h2_full, 1); mbar_init(y_full, 1); mbar_init(y_empty, 8);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    tma_prefetch_desc(&mZh); tma_prefetch_desc(&mW1h); tma_prefetch_desc(&mW2h); tma_prefetch_desc(&mWfh);
+    if (p.planes == 2) { tma_prefetch_desc(&mZl); tma_prefetch_desc(&mW1l); tma_prefetch_desc(&mW2l); tma_prefetch_desc(&mWfl); }
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_ptr_addr), "r"(TC_TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_addr));
+
+  if (warp == 0) {
+    // ============================================ TMA producer ============================================
+    uint32_t it = 0;
+    const bool prof_on = p.prof != nullptr && blockIdx.x == 0;
+    long long c_zempty = 0; const long long c_start = clock64();
+    FuRing rg{ringb, bar0, slot_bytes, (uint32_t)S, (uint32_t)p.planes, 0u, 0, prof_on};
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      const int m0 = tile * TC_BM;
+      FU_PROF(c_zempty, mbar_wait(z_empty, (it & 1u) ^ 1u));
+      if (elect_one()) {
+        mbar_expect_tx(z_full, (uint32_t)p.planes * 2 * PL);
+        for (int kb = 0; kb < 2; ++kb) {
+          tma_load_2d(zbuf(kb, 0), &mZh, z_full, kb * 64, m0);
+          if (p.planes == 2) tma_load_2d(zbuf(kb, 1), &mZl, z_full, kb * 64, m0);
+        }
+      }
+      __syncwarp();
+      // weight blocks in exactly the MMA issue order: G1_0 G1_1 { G2_c G1_{c+2} } G3z G3_c
+      for (int c = 0; c < 2; ++c)
+        for (int kb = 0; kb < 2; ++kb) rg.load(&mW1h, &mW1l, kb * 64, c * 64, PL / 2);
+      for (int c = 0; c < 6; ++c) {
+        for (int n = 0; n < 3; ++n) rg.load(&mW2h, &mW2l, c * 64, n * 128, PL);
+        if (c + 2 < 6)
+          for (int kb = 0; kb < 2; ++kb) rg.load(&mW1h, &mW1l, kb * 64, (c + 2) * 64, PL / 2);
+      }
+      for (int kb = 0; kb < 2; ++kb) rg.load(&mWfh, &mWfl, (6 + kb) * 64, 0, PL);   // G3z: Wfz
+      for (int c = 0; c < 6; ++c) rg.load(&mWfh, &mWfl, c * 64, 0, PL);             // G3_c: Wf
+    }
+    if (prof_on && lane == 0) { p.prof[0] = clock64() - c_start; p.prof[1] = rg.c_wait; p.prof[2] = c_zempty; p.prof[3] = it; }
+  } else if (warp == 1) {
+    // ============================================ MMA issuer ============================================
+    const uint32_t idesc64 = make_idesc_bf16(TC_BM, 64), idesc128 = make_idesc_bf16(TC_BM, 128);
+    uint32_t it = 0, n_af[2] = {0, 0};
+    const bool prof_on = p.prof != nullptr && blockIdx.x == 0;
+    long long c_afull = 0, c_tile0 = 0; const long long c_start = clock64();
+    FuRing rg{ringb, bar0, slot_bytes, (uint32_t)S, (uint32_t)p.planes, 0u, 0, prof_on};
+    // G1_c: T1[c&1] = z · W1z[64c:64c+64, :]^T  (two k-blocks of z)
+#define FU_G1(c_)                                                                                                            \
+  do {                                                                                                                       \
+    const int x_ = (c_) & 1;                                                                                                  \
+    rg.mma_ss(zbuf(0, 0), zbuf(0, 1), tmem_base + (uint32_t)(x_ * 64), idesc64, true);                                        \
+    rg.mma_ss(zbuf(1, 0), zbuf(1, 1), tmem_base + (uint32_t)(x_ * 64), idesc64, false);                                       \
+    tc_commit_elect(t1_full(x_));                                                                                             \
+  } while (0)
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      FU_PROF(c_tile0, mbar_wait(y_empty, (it & 1u) ^ 1u));        // previous tile's Y (= T1a|T1b) copied out by the LayerNorm warps
+      FU_PROF(c_tile0, mbar_wait(z_full, it & 1u));
+      tc_fence_after();
+      FU_G1(0);
+      FU_G1(1);
+      for (int c = 0; c < 6; ++c) {
+        const int x = c & 1;
+        FU_PROF(c_afull, mbar_wait(a_full(x), n_af[x] & 1u)); ++n_af[x];     // epilogue wrote h1_c (bf16 hi/lo) into T1[x]
+        tc_fence_after();
+#pragma unroll
+        for (int n = 0; n < 3; ++n) rg.mma_ts(tmem_base + (uint32_t)(x * 64), tmem_base + 128u + (uint32_t)(n * 128), idesc128, c == 0);
+        if (c == 5) tc_commit_elect(h2_full);
+        if (c + 2 < 6) FU_G1(c + 2);                               // overwrites T1[x]: ordered after G2_c by issue order
+      }
+      rg.mma_ss(zbuf(0, 0), zbuf(0, 1), tmem_base, idesc128, true);     // Y = z · Wfz^T   (T1 is free: G2_4/G2_5 precede in issue order)
+      rg.mma_ss(zbuf(1, 0), zbuf(1, 1), tmem_base, idesc128, false);
+      tc_commit_elect(z_empty);
+      for (int c = 0; c < 6; ++c) {
+        FU_PROF(c_afull, mbar_wait(a2_full(c), it & 1u));                    // epilogue wrote h2_c into H2's columns [64c, 64c+64)
+        tc_fence_after();
+        rg.mma_ts(tmem_base + 128u + (uint32_t)(c * 64), tmem_base, idesc128, false);
+      }
+      tc_commit_elect(y_full);
+    }
+#undef FU_G1
+    if (prof_on && lane == 0) { p.prof[8] = clock64() - c_start; p.prof[9] = rg.c_wait; p.prof[10] = c_afull; p.prof[12] = c_tile0; }
+  } else {
+    // ============================================ epilogue warps 2..9 ============================================
+    // Two independent groups of four warps (one warp per TMEM lane quadrant).  Group g owns T1[g]: it converts the h1 chunks
+    // c = g, g+2, g+4 and the h2 chunks of the same parity, a whole 64-column chunk per step per thread-row, so the two groups
+    // work on consecutive chunks concurrently and the MMA pipe always has the other group's chunk to consume.  Per-step fixed
+    // latencies (barrier wake-up, tcgen05.ld/st round trips) are what bound this path; fewer, larger steps amortise them.
+    const int quad = warp & 3, grp = (warp - 2) >> 2;
+    const int row = quad * 32 + lane;
+    const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16);
+    uint32_t it = 0, n_t1f = 0;
+    const bool prof_on = p.prof != nullptr && blockIdx.x == 0 && warp == 2;
+    long long c_t1f = 0, c_h2f = 0, c_yf = 0, c_ln = 0; const long long c_start = clock64();
+    // v[64] (fp32, this row's chunk) -> bf16 hi/lo images over the chunk's own 64 TMEM columns: hi words -> columns [0,32),
+    // lo words -> columns [32,64).  All reads of the fp32 columns by this thread precede the stores (same thread, in order).
+    auto write_a = [&](uint32_t tchunk, const float (&v)[64]) {
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        uint32_t h[16], l[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) split2_bf16(v[half * 32 + 2 * e], v[half * 32 + 2 * e + 1], h[e], l[e]);
+        tmem_st16(tchunk + (uint32_t)(16 * half), h);
+        if (p.planes == 2) tmem_st16(tchunk + 32u + (uint32_t)(16 * half), l);
+      }
+      tmem_st_wait();
+    };
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      const long long m = (long long)tile * TC_BM + row;
+      const bool valid0 = m < p.E;
+      const float* pP = nullptr; const float* pQ = nullptr;
+      float emask = 0.f;
+      if (valid0) {
+        const long long nn = (long long)p.nres * p.nres;
+        const long long b = m / nn;
+        const int rem = (int)(m - b * nn);
+        const int ri = rem / p.nres, rj = rem - ri * p.nres;
+        pP = p.pquv + (b * p.nres + ri) * ET_NODE;          // P at +0, U at +768
+        pQ = p.pquv + (b * p.nres + rj) * ET_NODE + ET_HID;  // Q at +384 (-> +0 here), V at +896 (-> +512 here)
+        emask = p.res_mask[b * p.nres + ri] * p.res_mask[b * p.nres + rj];
+      }
+      const bool valid = valid0 && !p.dbg_noq;
+      // ---- epi1: h1 chunks of this group's parity.  The per-row node term Q_j (L2 latency) is requested before the wait on
+      //      the accumulator, P_i (shared by the tile's rows, L1 hits) at use. ------------------------------------------------
+      for (int c = grp; c < 6; c += 2) {
+        float v[64];
+        const int col0 = c * 64;
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+          const float4 y4 = valid ? __ldg(reinterpret_cast<const float4*>(pQ + col0 + q * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          v[q * 4 + 0] = y4.x; v[q * 4 + 1] = y4.y; v[q * 4 + 2] = y4.z; v[q * 4 + 3] = y4.w;
+        }
+        FU_PROF(c_t1f, mbar_wait(t1_full(grp), n_t1f & 1u)); ++n_t1f;
+        tc_fence_after();
+        const uint32_t tchunk = trow + (uint32_t)(grp * 64);
+        {
+          uint32_t r0[32], r1[32];
+          tmem_ld32_nowait(tchunk, r0);
+          tmem_ld32_nowait(tchunk + 32u, r1);
+          tmem_ld_wait();
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float4 pa = valid ? __ldg(reinterpret_cast<const float4*>(pP + col0 + q * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4 pb = valid ? __ldg(reinterpret_cast<const float4*>(pP + col0 + 32 + q * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            v[q * 4 + 0] = fmaxf((__uint_as_float(r0[q * 4 + 0]) + pa.x) + v[q * 4 + 0], 0.f); v[q * 4 + 1] = fmaxf((__uint_as_float(r0[q * 4 + 1]) + pa.y) + v[q * 4 + 1], 0.f);
+            v[q * 4 + 2] = fmaxf((__uint_as_float(r0[q * 4 + 2]) + pa.z) + v[q * 4 + 2], 0.f); v[q * 4 + 3] = fmaxf((__uint_as_float(r0[q * 4 + 3]) + pa.w) + v[q * 4 + 3], 0.f);
+            v[32 + q * 4 + 0] = fmaxf((__uint_as_float(r1[q * 4 + 0]) + pb.x) + v[32 + q * 4 + 0], 0.f); v[32 + q * 4 + 1] = fmaxf((__uint_as_float(r1[q * 4 + 1]) + pb.y) + v[32 + q * 4 + 1], 0.f);
+            v[32 + q * 4 + 2] = fmaxf((__uint_as_float(r1[q * 4 + 2]) + pb.z) + v[32 + q * 4 + 2], 0.f); v[32 + q * 4 + 3] = fmaxf((__uint_as_float(r1[q * 4 + 3]) + pb.w) + v[32 + q * 4 + 3], 0.f);
+          }
+        }
+        write_a(tchunk, v);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(a_full(grp));
+      }
+      // ---- epi2: h2 chunks of this group's parity, in place over H2 -----------------------------------------------------
+      FU_PROF(c_h2f, mbar_wait(h2_full, it & 1u));
+      tc_fence_after();
+      for (int c = grp; c < 6; c += 2) {
+        float v[64];
+        const int col0 = c * 64;
+        const uint32_t tchunk = trow + 128u + (uint32_t)(c * 64);
+        {
+          uint32_t r0[32], r1[32];
+          tmem_ld32_nowait(tchunk, r0);
+          tmem_ld32_nowait(tchunk + 32u, r1);
+          tmem_ld_wait();
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float4 ba = __ldg(reinterpret_cast<const float4*>(p.b2 + col0 + q * 4));
+            const float4 bb = __ldg(reinterpret_cast<const float4*>(p.b2 + col0 + 32 + q * 4));
+            v[q * 4 + 0] = fmaxf(__uint_as_float(r0[q * 4 + 0]) + ba.x, 0.f); v[q * 4 + 1] = fmaxf(__uint_as_float(r0[q * 4 + 1]) + ba.y, 0.f);
+            v[q * 4 + 2] = fmaxf(__uint_as_float(r0[q * 4 + 2]) + ba.z, 0.f); v[q * 4 + 3] = fmaxf(__uint_as_float(r0[q * 4 + 3]) + ba.w, 0.f);
+            v[32 + q * 4 + 0] = fmaxf(__uint_as_float(r1[q * 4 + 0]) + bb.x, 0.f); v[32 + q * 4 + 1] = fmaxf(__uint_as_float(r1[q * 4 + 1]) + bb.y, 0.f);
+            v[32 + q * 4 + 2] = fmaxf(__uint_as_float(r1[q * 4 + 2]) + bb.z, 0.f); v[32 + q * 4 + 3] = fmaxf(__uint_as_float(r1[q * 4 + 3]) + bb.w, 0.f);
+          }
+        }
+        write_a(tchunk, v);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(a2_full(c));
+      }
+      // ---- epi3: LayerNorm + mask + store.  Warp (quad, grp) owns 64 of the row's 128 columns; the two partial (sum, sum of
+      //      squared deviations) pairs meet in smem.  Y is copied to registers and released at once so the next tile's G1 can
+      //      start; U_i + V_j are fetched before the wait. ------------------------------------------------------------------
+      {
+        float v[64];
+        const int cb = grp * 64;
+        if (valid) {
+          const float* pU = pP + 2 * ET_HID + cb;
+          const float* pV = pQ + (ET_HID + C_Z) + cb;   // pQ points at +384: V sits at 896 = 384 + 512
+#pragma unroll
+          for (int q = 0; q < 16; ++q) {
+            const float4 x4 = __ldg(reinterpret_cast<const float4*>(pU + q * 4));
+            const float4 y4 = __ldg(reinterpret_cast<const float4*>(pV + q * 4));
+            v[q * 4 + 0] = x4.x + y4.x; v[q * 4 + 1] = x4.y + y4.y; v[q * 4 + 2] = x4.z + y4.z; v[q * 4 + 3] = x4.w + y4.w;
+          }
+        } else {
+#pragma unroll
+          for (int q = 0; q < 64; ++q) v[q] = 0.f;
+        }
+        FU_PROF(c_yf, mbar_wait(y_full, it & 1u));
+        const long long c_ln0 = prof_on ? clock64() : 0;
+        tc_fence_after();
+        {
+          uint32_t r0[32], r1[32];
+          tmem_ld32_nowait(trow + (uint32_t)cb, r0);
+          tmem_ld32_nowait(trow + (uint32_t)(cb + 32), r1);
+          tmem_ld_wait();
+#pragma unroll
+          for (int q = 0; q < 32; ++q) { v[q] += __uint_as_float(r0[q]); v[32 + q] += __uint_as_float(r1[q]); }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(y_empty);
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+        for (int q = 0; q < 64; q += 4) { s0 += v[q]; s1 += v[q + 1]; s2 += v[q + 2]; s3 += v[q + 3]; }
+        const float psum = (s0 + s1) + (s2 + s3);
+        // stats buffer: [half 2][row 128][2] fp32 = 2 KB
+        const uint32_t st_mine = stats + (uint32_t)((grp * 128 + row) * 8), st_other = stats + (uint32_t)(((grp ^ 1) * 128 + row) * 8);
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(st_mine), "f"(psum) : "memory");
+        asm volatile("bar.sync %0, 64;" ::"r"(2 + quad) : "memory");     // the two warps of this quadrant
+        float osum;
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(osum) : "r"(st_other) : "memory");
+        const float mean = (psum + osum) * (1.f / 128.f);
+        float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
+#pragma unroll
+        for (int q = 0; q < 64; q += 4) {
+          const float d0 = v[q] - mean, d1 = v[q + 1] - mean, d2 = v[q + 2] - mean, d3 = v[q + 3] - mean;
+          q0 = fmaf(d0, d0, q0); q1 = fmaf(d1, d1, q1); q2 = fmaf(d2, d2, q2); q3 = fmaf(d3, d3, q3);
+        }
+        const float pvar = (q0 + q1) + (q2 + q3);
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(st_mine + 4), "f"(pvar) : "memory");
+        asm volatile("bar.sync %0, 64;" ::"r"(2 + quad) : "memory");
+        float ovar;
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(ovar) : "r"(st_other + 4) : "memory");
+        const float rstd = rsqrtf((pvar + ovar) * (1.f / 128.f) + 1e-5f);
+        if (valid) {
+#pragma unroll
+          for (int c0 = 0; c0 < 64; c0 += 8) {
+            const float4 g0 = __ldg(reinterpret_cast<const float4*>(p.ln_g + cb + c0)), g1v = __ldg(reinterpret_cast<const float4*>(p.ln_g + cb + c0 + 4));
+            const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.ln_b + cb + c0)), b1v = __ldg(reinterpret_cast<const float4*>(p.ln_b + cb + c0 + 4));
+            const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1v.x, g1v.y, g1v.z, g1v.w};
+            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1v.x, b1v.y, b1v.z, b1v.w};
+            uint32_t h[4], l[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              split2_bf16(((v[c0 + 2 * e] - mean) * rstd * gg[2 * e] + bb[2 * e]) * emask,
+                          ((v[c0 + 2 * e + 1] - mean) * rstd * gg[2 * e + 1] + bb[2 * e + 1]) * emask, h[e], l[e]);
+            *reinterpret_cast<uint4*>(p.out_hi + m * 128 + cb + c0) = make_uint4(h[0], h[1], h[2], h[3]);
+            if (p.planes == 2) *reinterpret_cast<uint4*>(p.out_lo + m * 128 + cb + c0) = make_uint4(l[0], l[1], l[2], l[3]);
+          }
+        }
+        if (prof_on) c_ln += clock64() - c_ln0;
+      }
+    }
+    if (prof_on && lane == 0) { p.prof[16] = clock64() - c_start; p.prof[17] = c_t1f; p.prof[19] = c_h2f; p.prof[20] = c_yf; p.prof[21] = c_ln; }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TC_TMEM_COLS) : "memory");
+  }
+}
+
 constexpr size_t TC_SMEM_BYTES = 1024 + (size_t)(TC_SA + TC_SB) * 2 * TC_PLANE_BYTES + 256;
 
 // planes -> fp32 (debug taps / export)
@@ -368,21 +866,25 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
 static PFN_encodeTiled g_encode = nullptr;
 static int g_tc_sms = 148;
 
+static long long* g_tc_prof = nullptr;   // device [32]; set by fd_debug_tc_profile
+static int g_tc_fused = 1;   // FD_TC_UNFUSED=1 selects the three-launch path (kept as the fused kernel's cross-check)
 inline int tc_init(int sm_count) {
   g_tc_sms = sm_count;
+  g_tc_fused = getenv("FD_TC_UNFUSED") ? 0 : 1;
   void* fn = nullptr;
   cudaDriverEntryPointQueryResult q;
   if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn) return -2;
   g_encode = (PFN_encodeTiled)fn;
   if (cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES) != cudaSuccess) return -2;
+  if (cudaFuncSetAttribute(tc_edge_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FU_SMEM_BYTES) != cudaSuccess) return -2;
   return 0;
 }
 
 // 2-D bf16 row-major [rows, cols] tensor map with a {64 cols, 128 rows} box and 128B swizzle
-inline int tc_make_map(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols) {
+inline int tc_make_map(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, int box_rows = TC_BM) {
   cuuint64_t dims[2] = {cols, rows};
   cuuint64_t strides[1] = {cols * 2};
-  cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)TC_BM};
+  cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
   cuuint32_t es[2] = {1, 1};
   CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, es,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -392,7 +894,8 @@ inline int tc_make_map(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t 
 
 struct TcMat {   // a bf16 hi/lo weight image [rows, cols] + maps
   __nv_bfloat16* hi = nullptr; __nv_bfloat16* lo = nullptr;
-  CUtensorMap mh, ml;
+  CUtensorMap mh, ml;         // box {64 k, 128 rows}
+  CUtensorMap mh64, ml64;     // box {64 k, 64 rows} (fused kernel's 64-unit hidden chunks)
   int rows = 0, cols = 0;
 };
 
@@ -464,6 +967,8 @@ inline int tc_pack_weights(TcWeights& tw, const std::map<std::string, const floa
   for (auto& it : items) {
     if (tc_make_map(&it.m->mh, it.m->hi, it.rows, it.cols)) return -2;
     if (tc_make_map(&it.m->ml, it.m->lo, it.rows, it.cols)) return -2;
+    if (tc_make_map(&it.m->mh64, it.m->hi, it.rows, it.cols, 64)) return -2;
+    if (tc_make_map(&it.m->ml64, it.m->lo, it.rows, it.cols, 64)) return -2;
   }
   tw.ready = true;
   return 0;
@@ -531,6 +1036,18 @@ inline int tc_edge_transition(const TcWeights& tw, TcWorkspace& w, int blk, int 
   const long long E = w.E;
   const int planes = prec == 1 ? 2 : 1;
   if (E > 0x7fffffffLL) return -1;
+  if (g_tc_fused) {
+    FusedParams f{};
+    f.E = (int)E; f.planes = planes; f.nres = N; f.num_tiles = (int)((E + TC_BM - 1) / TC_BM);
+    f.pquv = pquv; f.b2 = b2; f.ln_g = ln_g; f.ln_b = ln_b; f.res_mask = res_mask; f.out_hi = w.z_hi; f.out_lo = w.z_lo;
+    f.prof = g_tc_prof;
+    f.dbg_noq = getenv("FD_FU_NOQ") ? 1 : 0;
+    const int grid = f.num_tiles < g_tc_sms ? f.num_tiles : g_tc_sms;
+    tc_edge_fused_kernel<<<grid, FU_THREADS, FU_SMEM_BYTES, st>>>(w.m_z_h, w.m_z_l, tw.w1z[blk].mh64, tw.w1z[blk].ml64, tw.w2[blk].mh,
+                                                                 tw.w2[blk].ml, tw.wf[blk].mh, tw.wf[blk].ml, f);
+    if (launches) ++*launches;
+    return cudaGetLastError() == cudaSuccess ? 0 : -2;
+  }
   TcGemmParams p{};
   p.M = (int)E; p.N = ET_HID; p.KB0 = 2; p.KB1 = 0; p.planes = planes; p.epi = TC_EPI_RELU; p.rowadd = pquv; p.off_i = 0; p.off_j = ET_HID;
   p.ld_rowadd = ET_NODE; p.nres = N; p.out_hi = w.h1_hi; p.out_lo = w.h1_lo;

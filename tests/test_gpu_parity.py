@@ -55,7 +55,9 @@ def test_igso3_score_grid(eng):
     # … and max-norm per sigma row over the whole well-conditioned range (tiny omega: lo*dhi - hi*dlo cancels in fp32
     # in the reference itself, so only the absolute size is meaningful there)
     for r in range(T):
-        assert_close(sc[r][ok[r]], g["score"][r][ok[r]], 0, norm_rel=1e-4, name=f"igso3 score row {r}")
+        assert_close(sc[r][mid[r]], g["score"][r][mid[r]], 0, norm_rel=1e-4, name=f"igso3 score row {r}")
+        tiny = ok[r] & ~mid[r]      # omega < 0.05: reference value is fp32 cancellation noise; bound the absolute error
+        assert_close(sc[r][tiny], g["score"][r][tiny], 0, atol=1e-3 * np.abs(g["score"][r][ok[r]]).max(), name=f"igso3 tiny omega row {r}")
     assert np.all(np.isfinite(sc))
 
 
