@@ -402,7 +402,22 @@ extern "C" int fd_load_weights(fd_handle h, const float* const* P) {
   rel_table_kernel<<<2 * REL_DMAX + 1, 128, 0, h->stream>>>(W.ee_w0r, W.ee_T);
   CK(cudaGetLastError());
   // bf16 hi/lo images for the tensor-core edge kernels
-  if (tc_pack_weights(h->tcw, M, h->stream)) return fail(FD_ECUDA, "packing bf16 weight planes failed: %s", cudaGetErrorString(cudaGetLastError()));
+  {
+    std::vector<TcLinSpec> lins;
+    auto reg = [&](const Lin& L, int rows, int cols) { lins.push_back({L.w, pk.host.data() + (L.w - dbase), rows, cols}); };
+    reg(W.ne2, 256, 256); reg(W.ne4, 256, 256);
+    for (int b = 0; b < NBLK; ++b) {
+      const BlockW& X = W.blk[b];
+      reg(X.proj, PROJ_ALL, C_S); reg(X.out, C_S, IPA_FEAT);
+      for (int l = 0; l < TF_LAYERS; ++l) {
+        reg(X.tf[l].in_proj, 3 * TF_D, TF_D); reg(X.tf[l].out_proj, TF_D, TF_D); reg(X.tf[l].lin1, TF_D, TF_D); reg(X.tf[l].lin2, TF_D, TF_D);
+      }
+      reg(X.post, C_S, TF_D); reg(X.tr1, C_S, C_S); reg(X.tr2, C_S, C_S); reg(X.tr3, C_S, C_S);
+      if (b < NBLK - 1) { reg(X.et_init, C_Z, C_S); reg(X.et_node, ET_NODE, C_Z); }
+    }
+    reg(W.tor1, C_S, C_S); reg(W.tor2, C_S, C_S);
+    if (tc_pack_weights(h->tcw, M, lins, h->stream)) return fail(FD_ECUDA, "packing bf16 weight planes failed: %s", cudaGetErrorString(cudaGetLastError()));
+  }
   CK(cudaStreamSynchronize(h->stream));
   h->weights_loaded = true;
   return FD_OK;
@@ -492,6 +507,12 @@ struct Fwd {
   // y[M,N] = act(x[M,K] · W^T + b) (+ residual)
   void linear(const float* x, int ldx, const Lin& L, int K, int Nout, float* y, int ldy, long long M, bool relu = false,
               const float* residual = nullptr, int ldr = 0, const float* rowmask = nullptr) {
+    if (err) return;
+    if (h->precision != FD_PREC_FP32) {   // node-path linears on the tensor cores (split-bf16 operands, fp32 accumulate/output)
+      const int rc = tc_linear(h->tcw, w.tc, h->precision, x, ldx, L.w, L.b, K, Nout, y, ldy, M, relu, residual, ldr, rowmask, st, &h->launches);
+      if (rc == 0) return;
+      if (rc < 0) { err = fail(FD_ECUDA, "tensor-core linear launch failed: %s", cudaGetErrorString(cudaGetLastError())); return; }
+    }
     GemmArgs g;
     g.A = x; g.lda = ldx; g.B = L.w; g.ldb = K; g.C = y; g.ldc = ldy; g.M = (int)M; g.N = Nout; g.K = K;
     g.bias = L.b; g.relu = relu; g.residual = residual; g.ldr = ldr; g.rowmask = rowmask;

@@ -159,7 +159,7 @@ constexpr int TC_SA = 2, TC_SB = 4;                           // ring depths
 constexpr int TC_THREADS = 192;
 constexpr int TC_TMEM_COLS = 512;
 
-enum { TC_EPI_RELU = 0, TC_EPI_LN = 1 };
+enum { TC_EPI_RELU = 0, TC_EPI_LN = 1, TC_EPI_F32 = 2 };
 
 struct TcGemmParams {
   int M, N;                 // rows; output width (128 or 384)
@@ -173,6 +173,13 @@ struct TcGemmParams {
   const float* ln_g; const float* ln_b;
   __nv_bfloat16* out_hi; __nv_bfloat16* out_lo;   // [M,N] planes
   int num_tiles;
+  // node-path linears (TC_EPI_F32): a work item is (row tile, n-group of `nch` 128-column chunks); fp32 output
+  int m_tiles, nch;         // row tiles; chunks per work item (edge layers: nch = N/128, one group)
+  int n_valid;              // true output width (weight rows are padded to a multiple of 128)
+  float* out_f32; int ldo;
+  const float* residual; int ldr;
+  const float* rowmask;     // [M]
+  int relu;
 };
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -196,7 +203,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mA0h, const __grid_constant__
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int KB = p.KB0 + p.KB1;
-  const int NCH = p.N / TC_NC;
+  const int NCH = p.nch;
   const uint32_t stage_bytes = (uint32_t)p.planes * TC_PLANE_BYTES;
 
   if (threadIdx.x == 0) {
@@ -224,7 +231,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mA0h, const __grid_constant__
     {
       uint32_t ia = 0, ib = 0;   // running stage counters (whole warp runs the loop; one elected lane issues)
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        const int m0 = tile * TC_BM;
+        const int m0 = (tile % p.m_tiles) * TC_BM, n0 = (tile / p.m_tiles) * NCH * TC_NC;
         for (int kb = 0; kb < KB; ++kb) {
           const uint32_t sa = ia % TC_SA, pa = (ia / TC_SA) & 1u;
           mbar_wait(a_empty(sa), pa ^ 1u);
@@ -244,8 +251,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mA0h, const __grid_constant__
             const uint32_t dstB = b_ring + sb * 2 * TC_PLANE_BYTES;
             if (elect_one()) {
               mbar_expect_tx(b_full(sb), stage_bytes);
-              tma_load_2d(dstB, &mBh, b_full(sb), kb * TC_BK, c * TC_NC);
-              if (p.planes == 2) tma_load_2d(dstB + TC_PLANE_BYTES, &mBl, b_full(sb), kb * TC_BK, c * TC_NC);
+              tma_load_2d(dstB, &mBh, b_full(sb), kb * TC_BK, n0 + c * TC_NC);
+              if (p.planes == 2) tma_load_2d(dstB + TC_PLANE_BYTES, &mBl, b_full(sb), kb * TC_BK, n0 + c * TC_NC);
             }
             __syncwarp();
             ++ib;
@@ -296,7 +303,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mA0h, const __grid_constant__
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
       mbar_wait(tmem_full, it & 1u);
       tc_fence_after();
-      const long long m = (long long)tile * TC_BM + row_in_tile;
+      const long long m = (long long)(tile % p.m_tiles) * TC_BM + row_in_tile;
+      const int n0 = (tile / p.m_tiles) * NCH * TC_NC;
       const bool valid = m < p.M;
       const float* add_i = nullptr; const float* add_j = nullptr;
       float emask = 1.f;
@@ -312,7 +320,29 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mA0h, const __grid_constant__
         if (p.res_mask) emask = p.res_mask[b * p.nres + ri] * p.res_mask[b * p.nres + rj];
       }
       const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16);
-      if (p.epi == TC_EPI_RELU) {
+      if (p.epi == TC_EPI_F32) {
+        const float rm = (valid && p.rowmask) ? p.rowmask[m] : 1.f;
+        for (int c0 = 0; c0 < NCH * TC_NC; c0 += 32) {
+          uint32_t r[32];
+          tmem_ld32(trow + (uint32_t)c0, r);
+          const int n = n0 + c0;
+          if (valid && n < p.n_valid) {
+            float* orow = p.out_f32 + m * p.ldo + n;
+            const float* rrow = p.residual ? p.residual + m * p.ldr + n : nullptr;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              if (n + q * 4 < p.n_valid) {     // n_valid is a multiple of 4 for every node linear routed here
+                float4 v = make_float4(__uint_as_float(r[q * 4 + 0]), __uint_as_float(r[q * 4 + 1]), __uint_as_float(r[q * 4 + 2]), __uint_as_float(r[q * 4 + 3]));
+                if (p.bias) { const float4 b4 = *reinterpret_cast<const float4*>(p.bias + n + q * 4); v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w; }
+                if (p.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+                v.x *= rm; v.y *= rm; v.z *= rm; v.w *= rm;
+                if (rrow) { const float4 r4 = *reinterpret_cast<const float4*>(rrow + q * 4); v.x += r4.x; v.y += r4.y; v.z += r4.z; v.w += r4.w; }
+                *reinterpret_cast<float4*>(orow + q * 4) = v;
+              }
+            }
+          }
+        }
+      } else if (p.epi == TC_EPI_RELU) {
         for (int c0 = 0; c0 < p.N; c0 += 32) {
           uint32_t r[32];
           tmem_ld32(trow + (uint32_t)c0, r);
@@ -850,6 +880,22 @@ tc_edge_fused_kernel(const __grid_constant__ CUtensorMap mZh, const __grid_const
 
 constexpr size_t TC_SMEM_BYTES = 1024 + (size_t)(TC_SA + TC_SB) * 2 * TC_PLANE_BYTES + 256;
 
+// fp32 [M, ld] (first K columns) -> dense bf16 hi/lo planes [M, K]  (A operand of a node-path tensor-core linear)
+__global__ void split_planes_kernel(const float* __restrict__ x, int ld, long long M, int K, __nv_bfloat16* __restrict__ hi,
+                                    __nv_bfloat16* __restrict__ lo) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // one float4
+  const int k4 = K / 4;
+  if (i >= M * k4) return;
+  const long long m = i / k4;
+  const int k = (int)(i - m * k4) * 4;
+  const float4 v = *reinterpret_cast<const float4*>(x + m * ld + k);
+  uint32_t h0, l0, h1, l1;
+  split2_bf16(v.x, v.y, h0, l0);
+  split2_bf16(v.z, v.w, h1, l1);
+  *reinterpret_cast<uint2*>(hi + m * K + k) = make_uint2(h0, h1);
+  if (lo) *reinterpret_cast<uint2*>(lo + m * K + k) = make_uint2(l0, l1);
+}
+
 // planes -> fp32 (debug taps / export)
 __global__ void planes_to_f32_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo, float* __restrict__ out,
                                      long long n) {
@@ -902,6 +948,7 @@ struct TcMat {   // a bf16 hi/lo weight image [rows, cols] + maps
 struct TcWeights {
   bool ready = false;
   char* arena = nullptr;
+  std::map<const float*, TcMat> lin;   // node-path linears, keyed by the fp32 device weight pointer (rows padded to 128)
   TcMat ee2, ee4;                 // edge embedder layers 2 and 4: [128][128]
   TcMat w1z[3], w2[3], wf[3];     // EdgeTransition: [384][128], [384][384], [128][512] = [Wf | Wf[:, :128]]
 };
@@ -909,6 +956,9 @@ struct TcWeights {
 struct TcWorkspace {
   char* base = nullptr;
   long long E = 0;
+  long long R = 0;                                                  // node rows (B*N)
+  __nv_bfloat16 *a_hi = nullptr, *a_lo = nullptr;                    // node-linear A planes scratch [R, <= 2688]
+  std::map<int, std::pair<CUtensorMap, CUtensorMap>> a_maps;        // per K: maps over the scratch viewed as [R, K]
   __nv_bfloat16 *z_hi, *z_lo, *h1_hi, *h1_lo, *h2_hi, *h2_lo;
   CUtensorMap m_z_h, m_z_l, m_h1_h, m_h1_l, m_h2_h, m_h2_l;      // K = 128 / 384 / 384
   CUtensorMap m_e0_h, m_e0_l, m_e1_h, m_e1_l;                     // embedder staging viewed as [E,128] inside h1 / h2
@@ -927,10 +977,18 @@ static inline uint16_t f2bf(float f) {   // round-to-nearest-even, like __float2
 }
 static inline float bf2f(uint16_t h) { uint32_t u = (uint32_t)h << 16; float f; memcpy(&f, &u, 4); return f; }
 
-inline int tc_pack_weights(TcWeights& tw, const std::map<std::string, const float*>& M, cudaStream_t st) {
+struct TcLinSpec { const float* key; const float* host; int rows, cols; };   // fp32 device pointer (key), host image [rows, cols]
+
+inline int tc_pack_weights(TcWeights& tw, const std::map<std::string, const float*>& M, const std::vector<TcLinSpec>& lins, cudaStream_t st) {
   tc_free_weights(tw);
   struct Item { TcMat* m; std::vector<float> w; int rows, cols; };
   std::vector<Item> items;
+  for (const auto& L : lins) {      // node-path linears: pad the output dimension to a multiple of 128 with zero rows
+    const int prow = (L.rows + 127) / 128 * 128;
+    std::vector<float> w((size_t)prow * L.cols, 0.f);
+    memcpy(w.data(), L.host, (size_t)L.rows * L.cols * sizeof(float));
+    items.push_back({&tw.lin[L.key], std::move(w), prow, L.cols});
+  }
   auto add = [&](TcMat* m, const float* src, int rows, int cols) { items.push_back({m, std::vector<float>(src, src + (size_t)rows * cols), rows, cols}); };
   add(&tw.ee2, M.at("embedding_layer.edge_embedder.2.weight"), 128, 128);
   add(&tw.ee4, M.at("embedding_layer.edge_embedder.4.weight"), 128, 128);
@@ -974,10 +1032,12 @@ inline int tc_pack_weights(TcWeights& tw, const std::map<std::string, const floa
   return 0;
 }
 
+constexpr int TC_AMAX_K = IPA_FEAT;   // widest node-linear input (linear_out: 2688)
+inline size_t tc_hidden_width() { return getenv("FD_TC_UNFUSED") ? (size_t)ET_HID : (size_t)C_Z; }   // h1/h2 staging width
 inline size_t tc_workspace_bytes(int B, int N) {
-  const size_t E = (size_t)B * N * N;
+  const size_t E = (size_t)B * N * N, R = (size_t)B * N;
   auto al = [](size_t x) { return (x + 1023) & ~(size_t)1023; };
-  return 2 * al(E * C_Z * 2) + 4 * al(E * ET_HID * 2) + 1024;
+  return 2 * al(E * C_Z * 2) + 4 * al(E * tc_hidden_width() * 2) + 2 * al(R * TC_AMAX_K * 2) + 1024;
 }
 inline int tc_bind_workspace(TcWorkspace& w, char* p, int B, int N) {
   const size_t E = (size_t)B * N * N;
@@ -986,14 +1046,27 @@ inline int tc_bind_workspace(TcWorkspace& w, char* p, int B, int N) {
   w.base = p; w.E = (long long)E;
   w.z_hi = (__nv_bfloat16*)p; p += al(E * C_Z * 2);
   w.z_lo = (__nv_bfloat16*)p; p += al(E * C_Z * 2);
-  w.h1_hi = (__nv_bfloat16*)p; p += al(E * ET_HID * 2);
-  w.h1_lo = (__nv_bfloat16*)p; p += al(E * ET_HID * 2);
-  w.h2_hi = (__nv_bfloat16*)p; p += al(E * ET_HID * 2);
-  w.h2_lo = (__nv_bfloat16*)p; p += al(E * ET_HID * 2);
+  const size_t HW = tc_hidden_width();
+  w.h1_hi = (__nv_bfloat16*)p; p += al(E * HW * 2);
+  w.h1_lo = (__nv_bfloat16*)p; p += al(E * HW * 2);
+  w.h2_hi = (__nv_bfloat16*)p; p += al(E * HW * 2);
+  w.h2_lo = (__nv_bfloat16*)p; p += al(E * HW * 2);
+  w.R = (long long)B * N;
+  w.a_hi = (__nv_bfloat16*)p; p += al((size_t)w.R * TC_AMAX_K * 2);
+  w.a_lo = (__nv_bfloat16*)p; p += al((size_t)w.R * TC_AMAX_K * 2);
+  w.a_maps.clear();
   int rc = 0;
+  for (int K : {128, 256, 320, 384, IPA_FEAT}) {
+    std::pair<CUtensorMap, CUtensorMap> mp;
+    rc |= tc_make_map(&mp.first, w.a_hi, (uint64_t)w.R, (uint64_t)K);
+    rc |= tc_make_map(&mp.second, w.a_lo, (uint64_t)w.R, (uint64_t)K);
+    w.a_maps[K] = mp;
+  }
   rc |= tc_make_map(&w.m_z_h, w.z_hi, E, C_Z); rc |= tc_make_map(&w.m_z_l, w.z_lo, E, C_Z);
-  rc |= tc_make_map(&w.m_h1_h, w.h1_hi, E, ET_HID); rc |= tc_make_map(&w.m_h1_l, w.h1_lo, E, ET_HID);
-  rc |= tc_make_map(&w.m_h2_h, w.h2_hi, E, ET_HID); rc |= tc_make_map(&w.m_h2_l, w.h2_lo, E, ET_HID);
+  if (HW == (size_t)ET_HID) {   // three-launch cross-check path only
+    rc |= tc_make_map(&w.m_h1_h, w.h1_hi, E, ET_HID); rc |= tc_make_map(&w.m_h1_l, w.h1_lo, E, ET_HID);
+    rc |= tc_make_map(&w.m_h2_h, w.h2_hi, E, ET_HID); rc |= tc_make_map(&w.m_h2_l, w.h2_lo, E, ET_HID);
+  }
   rc |= tc_make_map(&w.m_e0_h, w.h1_hi, E, C_Z); rc |= tc_make_map(&w.m_e0_l, w.h1_lo, E, C_Z);
   rc |= tc_make_map(&w.m_e1_h, w.h2_hi, E, C_Z); rc |= tc_make_map(&w.m_e1_l, w.h2_lo, E, C_Z);
   return rc;
@@ -1001,7 +1074,9 @@ inline int tc_bind_workspace(TcWorkspace& w, char* p, int B, int N) {
 
 inline int tc_launch(const CUtensorMap& a0h, const CUtensorMap& a0l, const CUtensorMap& a1h, const CUtensorMap& a1l, const TcMat& Wt,
                      TcGemmParams p, cudaStream_t st, long long* launches) {
-  p.num_tiles = (p.M + TC_BM - 1) / TC_BM;
+  if (p.epi != TC_EPI_F32) {
+    p.m_tiles = (p.M + TC_BM - 1) / TC_BM; p.nch = p.N / TC_NC; p.num_tiles = p.m_tiles; p.n_valid = p.N;
+  }
   const int grid = p.num_tiles < g_tc_sms ? p.num_tiles : g_tc_sms;
   tc_gemm_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(a0h, a0l, a1h, a1l, Wt.mh, Wt.ml, p);
   if (launches) ++*launches;
@@ -1062,6 +1137,30 @@ inline int tc_edge_transition(const TcWeights& tw, TcWorkspace& w, int blk, int 
   r.out_hi = w.z_hi; r.out_lo = w.z_lo;
   if (tc_launch(w.m_h2_h, w.m_h2_l, w.m_z_h, w.m_z_l, tw.wf[blk], r, st, launches)) return -2;
   return 0;
+}
+
+// y[M, n_out] = act(x[M, K] · W^T + b) (* rowmask) (+ residual): node-path linear on the tensor cores.
+// Returns 1 if this linear is not registered / not eligible (caller uses the CUDA-core GEMM), 0 on success, <0 on error.
+inline int tc_linear(const TcWeights& tw, TcWorkspace& w, int prec, const float* x, int ldx, const float* wkey, const float* bias, int K,
+                     int n_out, float* y, int ldy, long long M, bool relu, const float* residual, int ldr, const float* rowmask,
+                     cudaStream_t st, long long* launches) {
+  auto it = tw.lin.find(wkey);
+  if (it == tw.lin.end() || K % TC_BK != 0 || K > TC_AMAX_K || M > w.R || n_out % 4 != 0 || ldx % 4 != 0) return 1;
+  auto mp = w.a_maps.find(K);
+  if (mp == w.a_maps.end()) return 1;
+  const int planes = prec == 1 ? 2 : 1;
+  const long long n4 = M * (K / 4);
+  split_planes_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(x, ldx, M, K, w.a_hi, planes == 2 ? w.a_lo : nullptr);
+  if (launches) ++*launches;
+  const TcMat& Wt = it->second;
+  TcGemmParams p{};
+  p.M = (int)M; p.N = Wt.rows; p.KB0 = K / TC_BK; p.KB1 = 0; p.planes = planes; p.epi = TC_EPI_F32; p.bias = bias;
+  p.m_tiles = (int)((M + TC_BM - 1) / TC_BM);
+  const int chunks = Wt.rows / TC_NC;
+  p.nch = (chunks % 2 == 0 && p.m_tiles * (chunks / 2) >= g_tc_sms) ? 2 : 1;    // wider work items once the grid is full anyway
+  p.num_tiles = p.m_tiles * (chunks / p.nch);
+  p.n_valid = n_out; p.out_f32 = y; p.ldo = ldy; p.residual = residual; p.ldr = ldr; p.rowmask = rowmask; p.relu = relu ? 1 : 0;
+  return tc_launch(mp->second.first, mp->second.second, mp->second.first, mp->second.second, Wt, p, st, launches);
 }
 
 inline void tc_export_z(TcWorkspace& w, float* z_f32, int prec, cudaStream_t st) {
