@@ -127,6 +127,17 @@ int fd_reverse_step(fd_handle h, int B, int N, float* rigids_io, const double* r
                     const double* z_rot, const double* z_trans, uint64_t seed, int64_t first_sample, int step,
                     float* rotmat_out, void* stream);
 
+/* SE3Diffuser.forward_marginal (se3_diffuser.py:43-110) for the n residues of one training example: noises rigids_0 [n,7]
+ * at time t with the caller's numpy draws (z_axis [n,3] = randn, u_angle [n] = rand, z_trans [n,3] = normal; fp64 device
+ * pointers), optional diffuse_mask [n].  Outputs rigids_t [n,7] fp32, rot_score / trans_score [n,3] fp64 (device) and the
+ * two score scalings (host scalars, may be NULL). */
+int fd_forward_marginal(fd_handle h, int64_t n, const float* rigids_0, double t, const double* z_axis, const double* u_angle,
+                        const double* z_trans, const float* diffuse_mask, float* rigids_t, double* rot_score, double* trans_score,
+                        double* rot_score_scaling, double* trans_score_scaling, void* stream);
+
+/* SE3Diffuser.score_scaling (se3_diffuser.py:155-158): host scalars. */
+int fd_score_scaling(fd_handle h, double t, double* rot_scaling, double* trans_scaling);
+
 /* all_atom.compute_backbone (data/all_atom.py:152-174): rigids [n,7] fp32 (Å) + psi [n,2] -> atom37 [n,37,3],
  * atom14 [n,14,3] (either may be NULL).  Device pointers. */
 int fd_compute_backbone(fd_handle h, int64_t n, const float* rigids, const float* psi, float* atom37, float* atom14,

@@ -90,6 +90,7 @@ struct fd_context {
   double* d_omega = nullptr;         // [1000]
   std::vector<double> h_sigma_grid;
   StepSched* d_sched1 = nullptr;     // single-entry schedule for fd_reverse_step
+  std::map<int, std::pair<double*, double>> igso3_rows;   // sigma index -> (device cdf row, rot score scaling), built lazily
   double* d_t_tmp = nullptr; size_t t_tmp_n = 0;
   bool debug = false;
   std::map<std::string, std::pair<void*, size_t>> dbg;
@@ -224,6 +225,7 @@ extern "C" int fd_destroy(fd_handle h) {
   cudaStreamSynchronize(h->stream);
   free_ws(h); free_lb(h);
   for (auto& kv : h->dbg) cudaFree(kv.second.first);
+  for (auto& kv : h->igso3_rows) cudaFree(kv.second.first);
   if (h->warena) cudaFree(h->warena);
   tc_free_weights(h->tcw);
   cudaFree(h->d_sigma_grid); cudaFree(h->d_cdf_t1); cudaFree(h->d_omega); cudaFree(h->d_sched1);
@@ -849,6 +851,63 @@ extern "C" int fd_reverse_step(fd_handle h, int B, int N, float* rigids_io, cons
   a.noise_stride = 0; a.rng_step_bias = step;   // single-entry schedule at index 0; Philox counters use the caller's step
   a.seed = seed; a.first_sample = first_sample; a.center = center; a.noise_scale = noise_scale; a.rotmat_out = rotmat_out; a.N = N;
   return launch_reverse(h, a, B, st);
+}
+
+// SE3Diffuser.forward_marginal (data/se3_diffuser.py:43-110) for n residues of one example.  Device pointers; noise injected
+// (the reference draws randn(n,3), rand(n) [SO3Diffuser.sample] then normal(n,3) [R3Diffuser.forward_marginal] from np.random).
+extern "C" int fd_forward_marginal(fd_handle h, int64_t n, const float* rigids_0, double t, const double* z_axis, const double* u_angle,
+                                   const double* z_trans, const float* diffuse_mask, float* rigids_t, double* rot_score, double* trans_score,
+                                   double* rot_score_scaling, double* trans_score_scaling, void* stream) {
+  if (!h || n <= 0 || !rigids_0 || !z_axis || !u_angle || !z_trans || !rigids_t || !rot_score || !trans_score)
+    return fail(FD_EINVAL, "fd_forward_marginal: bad argument");
+  if (!(t >= 0.0 && t <= 1.0)) return fail(FD_EINVAL, "Invalid t=%g", t);
+  CK(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const int idx = sigma_idx_host(h->h_sigma_grid, t);
+  // cdf row + score scaling for this sigma index: built on the GPU once and cached
+  auto it = h->igso3_rows.find(idx);
+  if (it == h->igso3_rows.end()) {
+    std::vector<double> cdf(SO3_NOMEGA);
+    double scal = 0;
+    CKI(build_igso3_rows(h, 1, &idx, nullptr, cdf.data(), nullptr, &scal));
+    double* d = nullptr;
+    CK(cudaMalloc(&d, SO3_NOMEGA * sizeof(double)));
+    CK(cudaMemcpy(d, cdf.data(), SO3_NOMEGA * sizeof(double), cudaMemcpyHostToDevice));
+    it = h->igso3_rows.emplace(idx, std::make_pair(d, scal)).first;
+  }
+  forward_marginal_kernel<<<(unsigned)((n + 7) / 8), 256, 0, st>>>(rigids_0, z_axis, u_angle, z_trans, diffuse_mask, t, h->h_sigma_grid[idx],
+                                                                 it->second.first, h->d_omega, rigids_t, rot_score, trans_score, n);
+  CK(cudaGetLastError());
+  if (rot_score_scaling) *rot_score_scaling = it->second.second;
+  if (trans_score_scaling) {
+    const double beta = t * R3_MIN_B + 0.5 * (t * t) * (R3_MAX_B - R3_MIN_B);
+    *trans_score_scaling = 1.0 / sqrt(1.0 - exp(-beta));
+  }
+  return FD_OK;
+}
+
+// SE3Diffuser.score_scaling (data/se3_diffuser.py:155-158): (rot, trans) scalings at time t; the IGSO(3) row is built on the GPU.
+extern "C" int fd_score_scaling(fd_handle h, double t, double* rot_scaling, double* trans_scaling) {
+  if (!h) return fail(FD_EINVAL, "null handle");
+  if (!(t >= 0.0 && t <= 1.0)) return fail(FD_EINVAL, "Invalid t=%g", t);
+  CK(cudaSetDevice(h->device));
+  const int idx = sigma_idx_host(h->h_sigma_grid, t);
+  auto it = h->igso3_rows.find(idx);
+  if (it == h->igso3_rows.end()) {
+    std::vector<double> cdf(SO3_NOMEGA);
+    double scal = 0;
+    CKI(build_igso3_rows(h, 1, &idx, nullptr, cdf.data(), nullptr, &scal));
+    double* d = nullptr;
+    CK(cudaMalloc(&d, SO3_NOMEGA * sizeof(double)));
+    CK(cudaMemcpy(d, cdf.data(), SO3_NOMEGA * sizeof(double), cudaMemcpyHostToDevice));
+    it = h->igso3_rows.emplace(idx, std::make_pair(d, scal)).first;
+  }
+  if (rot_scaling) *rot_scaling = it->second.second;
+  if (trans_scaling) {
+    const double beta = t * R3_MIN_B + 0.5 * (t * t) * (R3_MAX_B - R3_MIN_B);
+    *trans_scaling = 1.0 / sqrt(1.0 - exp(-beta));
+  }
+  return FD_OK;
 }
 
 extern "C" int fd_compute_backbone(fd_handle h, int64_t n, const float* rigids, const float* psi, float* atom37, float* atom14, void* stream) {

@@ -943,6 +943,88 @@ __global__ void sample_ref_kernel(const double* __restrict__ z_axis, const doubl
 }
 
 // ----------------------------------------------------------------------------------------------------------------
+// Forward noising of one example (SE3Diffuser.forward_marginal, data/se3_diffuser.py:43-110; SO3Diffuser.forward_marginal
+// so3_diffuser.py:311-328; R3Diffuser.forward_marginal r3_diffuser.py:81-101).  One warp per residue.
+//   rot:   axis = z_axis/|z_axis|, angle = interp(u, cdf_row(sigma_idx(t)), omega); s = axis*angle (fp64);
+//          rot_score = igso3 score of s (computed on the fp64->fp32 rounded s like the reference's torch.tensor(vec) path
+//          keeps fp64 — the reference calls torch_score on a float64 tensor here, so the whole series runs in fp64);
+//          R_t = R_0 · exp(s)
+//   trans: x_t ~ N(e^{-b/2}·0.1·x_0, 1 - e^{-b}) using z_trans; score = -(x_t - e^{-b/2} x_0s)/(1 - e^{-b}); x_t/0.1
+// ----------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double igso3_score_scalar_f64(double omega, double sigma, int lane) {
+  const double lo = sin(omega / 2), dlo = 0.5 * cos(omega / 2);
+  double psum = 0.0, dsum = 0.0;
+  for (int l = lane; l < IGSO3_L; l += 32) {
+    const double ex = -(double)((long long)l * (l + 1)) * (sigma * sigma) / 2.0;
+    if (ex < -745.2) break;
+    const double gauss = (double)(2 * l + 1) * exp(ex);
+    double hi, c;
+    sincos(omega * ((double)l + 0.5), &hi, &c);
+    const double dhi = ((double)l + 0.5) * c;
+    psum += gauss * hi / lo;
+    dsum += gauss * (lo * dhi - hi * dlo) / (lo * lo);
+  }
+  psum = warp_sum_d(psum);
+  dsum = warp_sum_d(dsum);
+  return dsum / (psum + 1e-4);
+}
+
+__global__ void __launch_bounds__(256) forward_marginal_kernel(
+    const float* __restrict__ rigids0, const double* __restrict__ z_axis, const double* __restrict__ u_angle,
+    const double* __restrict__ z_trans, const float* __restrict__ diffuse_mask, double t, double sigma, const double* __restrict__ cdf,
+    const double* __restrict__ omega_grid, float* __restrict__ rigids_t, double* __restrict__ rot_score, double* __restrict__ trans_score,
+    long long n) {
+  const int lane = threadIdx.x & 31;
+  const long long r = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (r >= n) return;
+  const double ax0 = z_axis[r * 3], ax1 = z_axis[r * 3 + 1], ax2 = z_axis[r * 3 + 2];
+  const double an = sqrt(ax0 * ax0 + ax1 * ax1 + ax2 * ax2);
+  const double u = u_angle[r];
+  double ang;
+  if (u <= cdf[0]) ang = omega_grid[0];
+  else if (u >= cdf[SO3_NOMEGA - 1]) ang = omega_grid[SO3_NOMEGA - 1];
+  else {
+    int lo = 0, hi = SO3_NOMEGA - 1;
+    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (cdf[mid] <= u) lo = mid; else hi = mid; }
+    ang = (omega_grid[lo + 1] - omega_grid[lo]) / (cdf[lo + 1] - cdf[lo]) * (u - cdf[lo]) + omega_grid[lo];
+  }
+  const double s[3] = {ax0 / an * ang, ax1 / an * ang, ax2 / an * ang};
+  // score of the sampled rotation vector (torch_score on a float64 tensor: omega = |s| + 1e-6, all fp64)
+  const double om = sqrt(s[0] * s[0] + s[1] * s[1] + s[2] * s[2]) + 1e-6;
+  const double sc = igso3_score_scalar_f64(om, sigma, lane);
+  const float dmf = diffuse_mask ? diffuse_mask[r] : 1.f;
+  const double dm = (double)dmf;
+  if (lane < 3) rot_score[r * 3 + lane] = dm * (sc * s[lane] / (om + 1e-6));
+  if (lane == 0) {
+    double q[4], n2 = 0.0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { q[k] = (double)rigids0[r * 7 + k]; n2 += q[k] * q[k]; }
+    const double inv = 1.0 / sqrt(n2);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) q[k] *= inv;
+    double e[4];
+    const double sh = ang < 1e-3 ? (0.5 - ang * ang / 48.0) : sin(ang * 0.5) / ang;
+    e[0] = cos(ang * 0.5); e[1] = sh * s[0]; e[2] = sh * s[1]; e[3] = sh * s[2];
+    double qn[4];
+    quat_mul(q, e, qn);
+    const double inv2 = 1.0 / sqrt(qn[0] * qn[0] + qn[1] * qn[1] + qn[2] * qn[2] + qn[3] * qn[3]);
+    const bool upd = dmf > 0.5f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) rigids_t[r * 7 + k] = (float)(upd ? qn[k] * inv2 : q[k]);
+    const double beta = t * R3_MIN_B + 0.5 * (t * t) * (R3_MAX_B - R3_MIN_B);
+    const double e1 = exp(-0.5 * beta), var = 1.0 - exp(-beta), sd = sqrt(var);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const double x0 = (double)__fmul_rn(rigids0[r * 7 + 4 + k], COORD_SCALE);   // numpy keeps fp32 for x_0 * 0.1
+      const double xt = e1 * x0 + sd * z_trans[r * 3 + k];
+      const double ts = -(xt - e1 * x0) / var;
+      trans_score[r * 3 + k] = dm * ts;
+      rigids_t[r * 7 + 4 + k] = (float)(dm * (xt / 0.1) + (1.0 - dm) * (double)rigids0[r * 7 + 4 + k]);
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------------------------------------------
 // IGSO(3) cache rows (SO3Diffuser.__init__, data/so3_diffuser.py:151-180), all fp64 like the numpy branch.
 // Kernel 1: block per (row, omega) computes the two L=1000 series.  Kernel 2: one thread per row does the
 // sequential cumsum (numpy order) and the score-scaling reduction.

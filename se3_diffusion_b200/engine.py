@@ -264,3 +264,66 @@ class FrameDiffEngine:
 
     def forward_flops(self, B, N, executed=True):
         return int(self.lib.fd_forward_flops(B, N, int(executed)))
+
+
+# ---- additional SE3Diffuser entry points (appended: forward_marginal / score_scaling / inference_fn) ------------------------
+def _forward_marginal(self, rigids_0: torch.Tensor, t: float, z_axis, u_angle, z_trans, diffuse_mask=None):
+    """fd_forward_marginal: noises one example [n,7] at time t with the caller's numpy draws.  Returns a dict of tensors on the
+    engine's device plus the two host scalings."""
+    dev = self.device
+    r0 = rigids_0.to(dev, torch.float32).contiguous().reshape(-1, 7)
+    n = r0.shape[0]
+    d64 = lambda a: torch.as_tensor(np.ascontiguousarray(a, dtype=np.float64)).to(dev)
+    za, ua, zt = d64(z_axis), d64(u_angle), d64(z_trans)
+    dm = None if diffuse_mask is None else torch.as_tensor(np.ascontiguousarray(diffuse_mask, dtype=np.float32)).to(dev).reshape(-1)
+    rt = torch.empty(n, 7, device=dev, dtype=torch.float32)
+    rs = torch.empty(n, 3, device=dev, dtype=torch.float64)
+    ts = torch.empty(n, 3, device=dev, dtype=torch.float64)
+    a, b = C.c_double(0), C.c_double(0)
+    st = torch.cuda.current_stream(dev)
+    check(self.lib.fd_forward_marginal(self._h, n, _ptr(r0), float(t), _ptr(za), _ptr(ua), _ptr(zt), _ptr(dm), _ptr(rt), _ptr(rs), _ptr(ts),
+                                       C.byref(a), C.byref(b), C.c_void_p(st.cuda_stream)))
+    st.synchronize()
+    return {"rigids_t": rt, "rot_score": rs, "trans_score": ts, "rot_score_scaling": a.value, "trans_score_scaling": b.value}
+
+
+def _score_scaling(self, t: float):
+    a, b = C.c_double(0), C.c_double(0)
+    check(self.lib.fd_score_scaling(self._h, float(t), C.byref(a), C.byref(b)))
+    return a.value, b.value
+
+
+def _inference_fn(self, data_init: dict, num_t: int = 500, min_t: float = 0.01, center: bool = True, aux_traj: bool = False,
+                  self_condition: bool = True, noise_scale: float = 1.0, noise: str = "numpy", seed: int = 123, first_sample: int = 0):
+    """Experiment.inference_fn (experiments/train_se3_diffusion.py:718-818) with the whole loop on the device.
+
+    data_init: the reference's feature dict (rigids_t [B,N,7] or [N,7], res_mask, fixed_mask, seq_idx).  noise="numpy" draws the
+    per-step Gaussians from the global numpy RNG in the reference's order (so np.random.seed(...) reproduces the reference's
+    trajectory); noise="philox" uses the on-device counter-based generator keyed by (seed, first_sample + b).
+    Returns the reference's dict: prot_traj [+ rigid_traj, trans_traj, psi_pred, rigid_0_traj when aux_traj].
+    """
+    rig = torch.as_tensor(data_init["rigids_t"]).detach().cpu().float()
+    if rig.ndim == 2:
+        rig = rig[None]
+    B, N = rig.shape[:2]
+    opt = lambda k, dt: None if k not in data_init else np.ascontiguousarray(torch.as_tensor(data_init[k]).detach().cpu().numpy().reshape(B, N), dtype=dt)
+    nz = None
+    if noise == "numpy" and num_t > 1:
+        zr = np.empty((num_t - 1, B, N, 3)); zx = np.empty((num_t - 1, B, N, 3))
+        for s in range(num_t - 1):           # SO(3) draw first, then R^3 (SE3Diffuser.reverse)
+            zr[s] = np.random.normal(size=(B, N, 3)); zx[s] = np.random.normal(size=(B, N, 3))
+        nz = {"z_rot": zr, "z_trans": zx}
+    out = self.sample(B, N, num_t=num_t, min_t=min_t, noise_scale=noise_scale, center=center, self_condition=self_condition,
+                      aux_traj=aux_traj, seed=seed, first_sample=first_sample, rigids_init=rig.numpy(), noise=nz,
+                      res_mask=opt("res_mask", np.float32), fixed_mask=opt("fixed_mask", np.float32), seq_idx=opt("seq_idx", np.int32))
+    ret = {"prot_traj": out["prot_traj"]}
+    if aux_traj:
+        ret.update({"rigid_traj": out["rigid_traj"], "trans_traj": out["trans_traj"], "psi_pred": torch.as_tensor(out["psi_pred"]),
+                    "rigid_0_traj": out["rigid_0_traj"]})
+    ret["_gpu_ms"] = out["gpu_ms"]
+    return ret
+
+
+FrameDiffEngine.forward_marginal = _forward_marginal
+FrameDiffEngine.score_scaling = _score_scaling
+FrameDiffEngine.inference_fn = _inference_fn

@@ -358,3 +358,93 @@ def test_tensor_core_large_tile_counts():
     e = engine("bf16x3")
     out = e.forward(f)
     _check_forward(out, ref, f["t"].numpy(), f["rigids_t"].numpy())
+
+
+# ---- reference-facing host API (se3_diffusion_b200.se3_diffuser.SE3Diffuser / score_network.ScoreNetwork) -------------------
+def _conf():
+    import sys, os
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import ref_harness as rh
+    return rh.default_conf()
+
+
+def test_diffuser_api_forward_marginal_and_scalings(eng):
+    """SE3Diffuser.forward_marginal through the mirror class, numpy RNG seeded like the reference run that made the golden."""
+    from se3_diffusion_b200.se3_diffuser import SE3Diffuser
+    g = golden("forward_marginal")
+    dif = SE3Diffuser(_conf()[1])
+    dif.bind_engine(eng)
+    for j in range(2):
+        t, use_mask, seed = g[f"cfg_{j}"]
+        np.random.seed(int(seed))
+        o = dif.forward_marginal(torch.tensor(g["rigids_0"]), float(t), diffuse_mask=g["mask"] if use_mask else None, as_tensor_7=True)
+        assert_close(fo.quat_to_rotmat(o["rigids_t"][..., :4]).numpy(), g[f"rot_{j}"], 0, atol=5e-6, name="rot_t")
+        assert_close(o["rigids_t"][..., 4:].numpy(), g[f"trans_{j}"], 0, norm_rel=2e-6, name="trans_t")
+        assert_close(o["trans_score"], g[f"trans_score_{j}"], 1e-7, atol=1e-9, name="trans_score")
+        om = np.linalg.norm(g[f"rot_score_{j}"], axis=-1)
+        assert_close(o["rot_score"], g[f"rot_score_{j}"], 0, norm_rel=1e-4, name="rot_score")
+        assert_close([o["trans_score_scaling"], o["rot_score_scaling"]], g[f"scal_{j}"], 1e-8, name="scalings")
+    gs = golden("schedules")
+    for k in (0, 137, 499):
+        rot, tr = dif.score_scaling(float(gs["t"][k]))
+        assert_close([rot, tr], [gs["rot_score_scaling"][k], gs["trans_score_scaling"][k]], 1e-8, name="score_scaling")
+    with pytest.raises(ValueError):
+        dif.score_scaling(1.5)
+
+
+def test_diffuser_api_reverse_and_sample_ref_follow_numpy_rng(eng):
+    from se3_diffusion_b200.se3_diffuser import SE3Diffuser
+    dif = SE3Diffuser(_conf()[1])
+    dif.bind_engine(eng)
+    g = golden("sample_ref")
+    np.random.seed(int(g["seed"]))
+    r = dif.sample_ref(int(g["n"]), as_tensor_7=True)["rigids_t"].numpy()
+    assert_close(quat_align(r[:, :4], g["rigids_t"][:, :4]), g["rigids_t"][:, :4], 0, atol=2e-6, name="sample_ref quat")
+    assert_close(r[:, 4:], g["rigids_t"][:, 4:], 1e-6, name="sample_ref trans")
+    g = golden("reverse_step")
+    for j in range(3):
+        t, use_mask, center, ns, seed = g[f"cfg_{j}"]
+        np.random.seed(int(seed))
+        out = dif.reverse(torch.tensor(g["rigids_t"]), g["rot_score"], g["trans_score"], float(t), float(g["dt"]),
+                          diffuse_mask=g["mask"] if use_mask else None, center=bool(center), noise_scale=float(ns))
+        out = out.to_tensor_7() if hasattr(out, "to_tensor_7") else out
+        assert_close(fo.quat_to_rotmat(out[..., :4].float().cpu()).numpy(), g[f"rot_{j}"], 0, atol=5e-6, name=f"reverse rot {j}")
+        assert_close(out[..., 4:].cpu().numpy(), g[f"trans_{j}"], 0, norm_rel=1e-6, name=f"reverse trans {j}")
+    with pytest.raises(ValueError):
+        dif.sample_ref(4, diffuse_mask=np.ones(4))          # "Must provide imputation values."
+
+
+def test_score_network_module_forward_matches_reference_golden():
+    """The nn.Module mirror (what the reference's Experiment wraps): state_dict in, reference-shaped dict out."""
+    from gpu_common import feats_from_golden, synthetic_state
+    from se3_diffusion_b200.score_network import ScoreNetwork
+    from se3_diffusion_b200.se3_diffuser import SE3Diffuser
+    mc, dc = _conf()
+    net = ScoreNetwork(mc, SE3Diffuser(dc), precision="bf16x3")
+    net.load_state_dict({k: torch.tensor(v) for k, v in synthetic_state(0).items()}, strict=True)
+    net = net.to("cuda").eval()
+    g = golden("forward_synth_1")
+    f = {k: v.to("cuda") for k, v in feats_from_golden(g).items()}
+    with torch.no_grad():
+        out = net(f)
+    assert set(out) == {"psi", "rot_score", "trans_score", "rigids", "atom37", "atom14"}
+    ref = {k[4:]: v for k, v in g.items() if k.startswith("out_")}
+    _check_forward(out, ref, g["in_t"], g["in_rigids_t"])
+    net.train()
+    with pytest.raises(NotImplementedError):
+        net(f)                                               # training path not built yet: loud, not silent
+
+
+def test_inference_fn_numpy_noise_matches_reference_golden(eng):
+    """Engine.inference_fn = Experiment.inference_fn: same np.random stream, same return dict, vs the reference run."""
+    g = golden("traj_synth")
+    B, N, num_t = int(g["B"]), int(g["N"]), int(g["num_t"])
+    np.random.seed(int(g["seed"]))
+    r7 = torch.stack([fo.sample_ref(N) for _ in range(B)])       # the caller draws the prior exactly like Sampler.sample
+    data = fo.init_feats(r7)
+    out = eng.inference_fn(data, num_t=num_t, min_t=0.01, aux_traj=True, noise_scale=float(g["noise_scale"]), noise="numpy")
+    for k in ("prot_traj", "rigid_traj", "trans_traj", "rigid_0_traj"):
+        assert out[k].shape == g[k].shape, k
+    assert tuple(out["psi_pred"].shape) == tuple(g["psi_pred"].shape)
+    assert_close(out["prot_traj"][-1], g["prot_traj"][-1], 0, norm_rel=TOL, name="step-1 atom37")
+    assert_close(out["rigid_traj"][-2][..., 4:], g["rigid_traj"][-2][..., 4:], 0, norm_rel=TOL, name="step-1 trans")
