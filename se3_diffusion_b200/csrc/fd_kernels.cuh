@@ -468,6 +468,110 @@ __global__ void __launch_bounds__(256) ipa_edge_kernel(
   }
 }
 
+// ----------------------------------------------------------------------------------------------------------------
+// IPA edge pass, tensor-core modes: the pair bias z·Wb^T (+bb) arrives precomputed from a tcgen05 GEMM over the z planes
+// (`pbias` [E, 8] fp32), so z is streamed ONCE here (Σ_j a·z).  One CTA per query residue (b,i), 256 threads:
+//   phase 1  thread (j mod 32, h): logits[h][j] = qk + sqrt(1/3)·pbias − ½γ_h·Σ_p|qp_i − kp_j|² + mask     (coalesced kp / pbias)
+//   phase 2  warp h: softmax over j, probabilities back to L
+//   phase 3  warp w: edges j ≡ w (mod 8), lane = 4 channels: zbar_w[h][c] += a[h][j]·z[i][j][c]; cross-warp sum in smem
+//   phase 4  o_pair = Wd·zbar + bd
+// ----------------------------------------------------------------------------------------------------------------
+template <int ZMODE>
+__global__ void __launch_bounds__(256) ipa_edge2_kernel(
+    const ZRef z, float* __restrict__ L, const float* __restrict__ pbias, const float* __restrict__ qp, const float* __restrict__ kp,
+    const float* __restrict__ res_mask, const float* __restrict__ gamma, const float* __restrict__ WdT, const float* __restrict__ bd,
+    float* __restrict__ feats, int N, int Np) {
+  extern __shared__ __align__(16) float sm[];
+  float* lg = sm;                         // [H][Np]
+  float* zb = lg + H * Np;                // [8 warps][H][128]
+  const int i = blockIdx.x, b = blockIdx.y;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long long rowi = (long long)b * N + i;
+  const float mi = res_mask[rowi];
+  for (int idx = tid; idx < H * Np; idx += 256) {
+    const int h = idx / Np, j = idx - h * Np;
+    lg[idx] = j < N ? L[(((long long)b * H + h) * N + i) * Np + j] : 0.f;
+  }
+  {  // phase 1
+    const int h = tid & 7, jl = tid >> 3;
+    float q[PQ * 3];
+#pragma unroll
+    for (int e = 0; e < PQ * 3; ++e) q[e] = qp[rowi * (H * PQ * 3) + h * (PQ * 3) + e];
+    const float g = gamma[h];
+    __syncthreads();
+    for (int j = jl; j < N; j += 32) {
+      const float4* kj = reinterpret_cast<const float4*>(kp + ((long long)b * N + j) * (H * PQ * 3) + h * (PQ * 3));
+      float d2 = 0.f;
+#pragma unroll
+      for (int e4 = 0; e4 < 6; ++e4) {
+        const float4 k4 = kj[e4];
+        const float e0 = q[e4 * 4 + 0] - k4.x, e1 = q[e4 * 4 + 1] - k4.y, e2 = q[e4 * 4 + 2] - k4.z, e3 = q[e4 * 4 + 3] - k4.w;
+        d2 += e0 * e0 + e1 * e1 + e2 * e2 + e3 * e3;
+      }
+      const float pb = pbias[(rowi * N + j) * H + h];
+      const float mj = res_mask[(long long)b * N + j];
+      float v = lg[h * Np + j];
+      v += 0.57735026918962576f * pb;
+      v += -0.5f * (g * d2);
+      v += 1e5f * (mi * mj - 1.f);
+      lg[h * Np + j] = v;
+    }
+  }
+  __syncthreads();
+  {  // phase 2: softmax, warp <-> head
+    float* row = lg + warp * Np;
+    float mx = -INFINITY;
+    for (int j = lane; j < N; j += 32) mx = fmaxf(mx, row[j]);
+    mx = warp_max(mx);
+    float s = 0.f;
+    for (int j = lane; j < N; j += 32) { const float e = expf(row[j] - mx); row[j] = e; s += e; }
+    s = warp_sum(s);
+    const float inv = 1.f / s;
+    float* Lrow = L + (((long long)b * H + warp) * N + i) * Np;
+    for (int j = lane; j < Np; j += 32) { const float a = j < N ? row[j] * inv : 0.f; row[j] = a; Lrow[j] = a; }
+  }
+  __syncthreads();
+  {  // phase 3
+    float acc[H][4];
+#pragma unroll
+    for (int h = 0; h < H; ++h) { acc[h][0] = 0.f; acc[h][1] = 0.f; acc[h][2] = 0.f; acc[h][3] = 0.f; }
+    const long long zrow = rowi * N * C_Z;
+    for (int j = warp; j < N; j += 8) {
+      const float4 zv = z_load4<ZMODE>(z, zrow + (long long)j * C_Z + lane * 4);
+#pragma unroll
+      for (int h = 0; h < H; ++h) {
+        const float a = lg[h * Np + j];
+        acc[h][0] = fmaf(a, zv.x, acc[h][0]); acc[h][1] = fmaf(a, zv.y, acc[h][1]);
+        acc[h][2] = fmaf(a, zv.z, acc[h][2]); acc[h][3] = fmaf(a, zv.w, acc[h][3]);
+      }
+    }
+#pragma unroll
+    for (int h = 0; h < H; ++h) *reinterpret_cast<float4*>(zb + (warp * H + h) * C_Z + lane * 4) = make_float4(acc[h][0], acc[h][1], acc[h][2], acc[h][3]);
+  }
+  __syncthreads();
+  // reduce the 8 per-warp partials: thread -> (h, 4 channels)
+  {
+    const int h = tid >> 5, c4 = (tid & 31) * 4;
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+      const float4 v = *reinterpret_cast<const float4*>(zb + (w * H + h) * C_Z + c4);
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+    __syncthreads();
+    *reinterpret_cast<float4*>(zb + h * C_Z + c4) = s;
+  }
+  __syncthreads();
+  {  // phase 4
+    const int h = tid >> 5, d = tid & 31;
+    float acc = bd[d];
+    const float* z0 = zb + h * C_Z;
+#pragma unroll 8
+    for (int c = 0; c < C_Z; ++c) acc = fmaf(WdT[c * 32 + d], z0[c], acc);
+    feats[rowi * IPA_FEAT + (H * C_HID + 4 * H * PV) + h * 32 + d] = acc;
+  }
+}
+
 // o_pt: global -> local frame, norms (model/ipa_pytorch.py:437-447; Rigid.invert_apply rigid_utils.py:1118).
 // optg [B*N, H*PV*3] (global-frame Σ_j a v_pts) -> feats columns [2048 .. 2432): x | y | z | norm, index h*12+p.
 __global__ void ipa_finish_kernel(const float* __restrict__ optg, const float* __restrict__ quat,

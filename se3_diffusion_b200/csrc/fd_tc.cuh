@@ -180,6 +180,7 @@ struct TcGemmParams {
   const float* residual; int ldr;
   const float* rowmask;     // [M]
   int relu;
+  const float* wb; const float* wb_bias; float* pbias;   // LN epilogue only: next IPA block's linear_b -> pair bias [M,8]
 };
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -200,9 +201,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mA0h, const __grid_constant__
   const uint32_t tmem_full = bar0 + 8u * (2 * TC_SA + 2 * TC_SB);
   const uint32_t tmem_empty = tmem_full + 8u;
   const uint32_t tmem_ptr_addr = tmem_empty + 8u;
+  const uint32_t wb_smem = bar0 + 256u;           // optional linear_b image [8][128] fp32 (LN epilogue's pair bias)
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int KB = p.KB0 + p.KB1;
+  if (p.pbias)
+    for (int i = threadIdx.x; i < H * C_Z; i += TC_THREADS) asm volatile("st.shared.f32 [%0], %1;" ::"r"(wb_smem + 4u * i), "f"(p.wb[i]) : "memory");
   const int NCH = p.nch;
   const uint32_t stage_bytes = (uint32_t)p.planes * TC_PLANE_BYTES;
 
@@ -411,6 +415,25 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mA0h, const __grid_constant__
             *reinterpret_cast<uint4*>(p.out_hi + m * 128 + c0) = *reinterpret_cast<const uint4*>(hi);
             if (p.planes == 2) *reinterpret_cast<uint4*>(p.out_lo + m * 128 + c0) = *reinterpret_cast<const uint4*>(lo);
           }
+          if (p.pbias) {      // pair bias of the first IPA block from the freshly normalised row (fp32); linear_b staged in smem
+            float pb[H];
+#pragma unroll
+            for (int hh = 0; hh < H; ++hh) pb[hh] = __ldg(p.wb_bias + hh);
+#pragma unroll
+            for (int c = 0; c < 128; c += 4) {
+              const float4 g4 = __ldg(reinterpret_cast<const float4*>(p.ln_g + c)), b4 = __ldg(reinterpret_cast<const float4*>(p.ln_b + c));
+              const float y0 = ((v[c] - mean) * rstd * g4.x + b4.x) * emask, y1 = ((v[c + 1] - mean) * rstd * g4.y + b4.y) * emask;
+              const float y2 = ((v[c + 2] - mean) * rstd * g4.z + b4.z) * emask, y3 = ((v[c + 3] - mean) * rstd * g4.w + b4.w) * emask;
+#pragma unroll
+              for (int hh = 0; hh < H; ++hh) {
+                float w0, w1, w2, w3;
+                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(w0), "=f"(w1), "=f"(w2), "=f"(w3) : "r"(wb_smem + 4u * (uint32_t)(hh * C_Z + c)));
+                pb[hh] += (y0 * w0 + y1 * w1) + (y2 * w2 + y3 * w3);
+              }
+            }
+            *reinterpret_cast<float4*>(p.pbias + m * H) = make_float4(pb[0], pb[1], pb[2], pb[3]);
+            *reinterpret_cast<float4*>(p.pbias + m * H + 4) = make_float4(pb[4], pb[5], pb[6], pb[7]);
+          }
         }
       }
       tc_fence_before();
@@ -561,14 +584,15 @@ struct FuRing {
 };
 
 constexpr int FU_THREADS = 320;   // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two groups of four)
-constexpr int FU_RING_BYTES = 160 * 1024;
-constexpr size_t FU_SMEM_BYTES = 64 * 1024 + FU_RING_BYTES + 512 + 2048;   // dynamic smem starts 1024-aligned (no static smem here)
+constexpr int FU_RING_BYTES = 128 * 1024;
+constexpr size_t FU_SMEM_BYTES = 64 * 1024 + FU_RING_BYTES + 512 + 2048 + 4096 + 8192;   // + Wb [8][128] + pair-bias partials [2][128][8]   // dynamic smem starts 1024-aligned (no static smem here)
 
 struct FusedParams {
   int E, planes, nres, num_tiles;
   const float* pquv;        // [B*nres, 1024] = P | Q | U | V node terms
   const float* b2; const float* ln_g; const float* ln_b; const float* res_mask;
   __nv_bfloat16* out_hi; __nv_bfloat16* out_lo;
+  const float* wb; const float* wb_bias; float* pbias;   // next IPA block's linear_b [8][128], [8] -> pair bias [E,8] (fp32) emitted by the LN epilogue
   long long* prof;          // optional [32] cycle counters written by CTA 0 (developer aid)
   int dbg_noq;              // developer experiment: skip the node-term loads (results wrong; isolates their cost)
 };
@@ -589,7 +613,7 @@ tc_edge_fused_kernel(const __grid_constant__ CUtensorMap mZh, const __grid_const
   const uint32_t zb = base;                              // z(kb, plane) = zb + (kb*2 + plane)*PL
   const uint32_t ringb = zb + 4 * PL;
   const uint32_t bar0 = ringb + FU_RING_BYTES;
-  const int S = p.planes == 2 ? 5 : 10;
+  const int S = p.planes == 2 ? 4 : 8;
   const uint32_t slot_bytes = (uint32_t)p.planes * PL;
   auto zbuf = [&](int kb, int pl) { return zb + (uint32_t)(kb * 2 + pl) * PL; };
   // barriers: ring full[10] (slots 0..9), ring empty[10] (10..19), then the named ones
@@ -600,6 +624,8 @@ tc_edge_fused_kernel(const __grid_constant__ CUtensorMap mZh, const __grid_const
   auto a2_full = [&](int c) { return bar0 + 8u * (29 + c); };      // one per h2 chunk (no back-pressure on epi2: avoid 2-phase run-ahead)
   const uint32_t tmem_ptr_addr = bar0 + 8u * 35;
   const uint32_t stats = bar0 + 512u;     // LayerNorm partial statistics [2][128 rows][2] fp32 = 2 KB
+  const uint32_t wb_s = stats + 2048u;    // linear_b weights [8][128] fp32
+  const uint32_t pb_s = wb_s + 4096u;     // pair-bias partials [2 halves][128 rows][8] fp32
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // warp-uniform by construction
   if (threadIdx.x == 0) {
@@ -615,6 +641,9 @@ tc_edge_fused_kernel(const __grid_constant__ CUtensorMap mZh, const __grid_const
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_ptr_addr), "r"(TC_TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (p.pbias && threadIdx.x >= 64) {
+    for (int i = threadIdx.x - 64; i < H * C_Z; i += FU_THREADS - 64) asm volatile("st.shared.f32 [%0], %1;" ::"r"(wb_s + 4u * i), "f"(p.wb[i]) : "memory");
   }
   tc_fence_before();
   __syncthreads();
@@ -849,6 +878,9 @@ tc_edge_fused_kernel(const __grid_constant__ CUtensorMap mZh, const __grid_const
         float ovar;
         asm volatile("ld.shared.f32 %0, [%1];" : "=f"(ovar) : "r"(st_other + 4) : "memory");
         const float rstd = rsqrtf((pvar + ovar) * (1.f / 128.f) + 1e-5f);
+        float pb[H];
+#pragma unroll
+        for (int hh = 0; hh < H; ++hh) pb[hh] = 0.f;
         if (valid) {
 #pragma unroll
           for (int c0 = 0; c0 < 64; c0 += 8) {
@@ -856,14 +888,41 @@ tc_edge_fused_kernel(const __grid_constant__ CUtensorMap mZh, const __grid_const
             const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.ln_b + cb + c0)), b1v = __ldg(reinterpret_cast<const float4*>(p.ln_b + cb + c0 + 4));
             const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1v.x, g1v.y, g1v.z, g1v.w};
             const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1v.x, b1v.y, b1v.z, b1v.w};
+            float y[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) y[e] = ((v[c0 + e] - mean) * rstd * gg[e] + bb[e]) * emask;
             uint32_t h[4], l[4];
 #pragma unroll
-            for (int e = 0; e < 4; ++e)
-              split2_bf16(((v[c0 + 2 * e] - mean) * rstd * gg[2 * e] + bb[2 * e]) * emask,
-                          ((v[c0 + 2 * e + 1] - mean) * rstd * gg[2 * e + 1] + bb[2 * e + 1]) * emask, h[e], l[e]);
+            for (int e = 0; e < 4; ++e) split2_bf16(y[2 * e], y[2 * e + 1], h[e], l[e]);
             *reinterpret_cast<uint4*>(p.out_hi + m * 128 + cb + c0) = make_uint4(h[0], h[1], h[2], h[3]);
             if (p.planes == 2) *reinterpret_cast<uint4*>(p.out_lo + m * 128 + cb + c0) = make_uint4(l[0], l[1], l[2], l[3]);
+            if (p.pbias) {     // next IPA block's pair bias: partial dots of this thread's 64 channels with linear_b (smem, broadcast reads)
+#pragma unroll
+              for (int hh = 0; hh < H; ++hh) {
+                float w0, w1, w2, w3, w4, w5, w6, w7;
+                const uint32_t wa = wb_s + 4u * (uint32_t)(hh * C_Z + cb + c0);
+                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(w0), "=f"(w1), "=f"(w2), "=f"(w3) : "r"(wa));
+                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(w4), "=f"(w5), "=f"(w6), "=f"(w7) : "r"(wa + 16u));
+                pb[hh] += (y[0] * w0 + y[1] * w1) + (y[2] * w2 + y[3] * w3) + (y[4] * w4 + y[5] * w5) + (y[6] * w6 + y[7] * w7);
+              }
+            }
           }
+        }
+        if (p.pbias) {       // the two column halves of a row meet in smem; group 0 writes the row's 8 biases
+          const uint32_t pm = pb_s + (uint32_t)((grp * 128 + row) * 32);
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(pm), "f"(pb[0]), "f"(pb[1]), "f"(pb[2]), "f"(pb[3]) : "memory");
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(pm + 16u), "f"(pb[4]), "f"(pb[5]), "f"(pb[6]), "f"(pb[7]) : "memory");
+          asm volatile("bar.sync %0, 64;" ::"r"(2 + quad) : "memory");
+          if (grp == 0 && valid) {
+            const uint32_t po = pb_s + (uint32_t)((128 + row) * 32);
+            float o0, o1, o2, o3, o4, o5, o6, o7;
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(o0), "=f"(o1), "=f"(o2), "=f"(o3) : "r"(po));
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(o4), "=f"(o5), "=f"(o6), "=f"(o7) : "r"(po + 16u));
+            const float4 bA = __ldg(reinterpret_cast<const float4*>(p.wb_bias)), bB = __ldg(reinterpret_cast<const float4*>(p.wb_bias + 4));
+            *reinterpret_cast<float4*>(p.pbias + m * H) = make_float4(pb[0] + o0 + bA.x, pb[1] + o1 + bA.y, pb[2] + o2 + bA.z, pb[3] + o3 + bA.w);
+            *reinterpret_cast<float4*>(p.pbias + m * H + 4) = make_float4(pb[4] + o4 + bB.x, pb[5] + o5 + bB.y, pb[6] + o6 + bB.z, pb[7] + o7 + bB.w);
+          }
+          asm volatile("bar.sync %0, 64;" ::"r"(2 + quad) : "memory");   // partial slots are reused by the next tile
         }
         if (prof_on) c_ln += clock64() - c_ln0;
       }
@@ -878,7 +937,7 @@ tc_edge_fused_kernel(const __grid_constant__ CUtensorMap mZh, const __grid_const
   }
 }
 
-constexpr size_t TC_SMEM_BYTES = 1024 + (size_t)(TC_SA + TC_SB) * 2 * TC_PLANE_BYTES + 256;
+constexpr size_t TC_SMEM_BYTES = 1024 + (size_t)(TC_SA + TC_SB) * 2 * TC_PLANE_BYTES + 256 + 4096;
 
 // fp32 [M, ld] (first K columns) -> dense bf16 hi/lo planes [M, K]  (A operand of a node-path tensor-core linear)
 __global__ void split_planes_kernel(const float* __restrict__ x, int ld, long long M, int K, __nv_bfloat16* __restrict__ hi,
@@ -923,6 +982,8 @@ inline int tc_init(int sm_count) {
   g_encode = (PFN_encodeTiled)fn;
   if (cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES) != cudaSuccess) return -2;
   if (cudaFuncSetAttribute(tc_edge_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FU_SMEM_BYTES) != cudaSuccess) return -2;
+  if (cudaFuncSetAttribute(ipa_edge2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) return -2;
+  if (cudaFuncSetAttribute(ipa_edge2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) return -2;
   return 0;
 }
 
@@ -958,6 +1019,7 @@ struct TcWorkspace {
   long long E = 0;
   long long R = 0;                                                  // node rows (B*N)
   __nv_bfloat16 *a_hi = nullptr, *a_lo = nullptr;                    // node-linear A planes scratch [R, <= 2688]
+  float* pbias = nullptr;                                            // IPA pair bias [E, 8] fp32
   std::map<int, std::pair<CUtensorMap, CUtensorMap>> a_maps;        // per K: maps over the scratch viewed as [R, K]
   __nv_bfloat16 *z_hi, *z_lo, *h1_hi, *h1_lo, *h2_hi, *h2_lo;
   CUtensorMap m_z_h, m_z_l, m_h1_h, m_h1_l, m_h2_h, m_h2_l;      // K = 128 / 384 / 384
@@ -1037,7 +1099,7 @@ inline size_t tc_hidden_width() { return getenv("FD_TC_UNFUSED") ? (size_t)ET_HI
 inline size_t tc_workspace_bytes(int B, int N) {
   const size_t E = (size_t)B * N * N, R = (size_t)B * N;
   auto al = [](size_t x) { return (x + 1023) & ~(size_t)1023; };
-  return 2 * al(E * C_Z * 2) + 4 * al(E * tc_hidden_width() * 2) + 2 * al(R * TC_AMAX_K * 2) + 1024;
+  return 2 * al(E * C_Z * 2) + 4 * al(E * tc_hidden_width() * 2) + 2 * al(R * TC_AMAX_K * 2) + al(E * H * 4) + 1024;
 }
 inline int tc_bind_workspace(TcWorkspace& w, char* p, int B, int N) {
   const size_t E = (size_t)B * N * N;
@@ -1054,6 +1116,7 @@ inline int tc_bind_workspace(TcWorkspace& w, char* p, int B, int N) {
   w.R = (long long)B * N;
   w.a_hi = (__nv_bfloat16*)p; p += al((size_t)w.R * TC_AMAX_K * 2);
   w.a_lo = (__nv_bfloat16*)p; p += al((size_t)w.R * TC_AMAX_K * 2);
+  w.pbias = (float*)p; p += al(E * H * 4);
   w.a_maps.clear();
   int rc = 0;
   for (int K : {128, 256, 320, 384, IPA_FEAT}) {
@@ -1086,7 +1149,8 @@ inline int tc_launch(const CUtensorMap& a0h, const CUtensorMap& a0l, const CUten
 // Edge embedder (model/score_network.py:79-86): layer 0 = table lookup kernel -> bf16 planes; layers 2, 4 on tensor cores.
 inline int tc_edge_embed(const TcWeights& tw, TcWorkspace& w, int prec, const float* AC, const float* T, const float* D, const float* w0r,
                          const int* seq_idx, const float* sc_ca, const float* res_mask, const float* b2, const float* b4,
-                         const float* ln_g, const float* ln_b, int B, int N, cudaStream_t st, long long* launches) {
+                         const float* ln_g, const float* ln_b, const float* next_wb, const float* next_bb, int B, int N, cudaStream_t st,
+                         long long* launches) {
   const long long E = w.E;
   const int planes = prec == 1 ? 2 : 1;
   if (E > 0x7fffffffLL) return -1;
@@ -1100,6 +1164,7 @@ inline int tc_edge_embed(const TcWeights& tw, TcWorkspace& w, int prec, const fl
   TcGemmParams q{};
   q.M = (int)E; q.N = 128; q.KB0 = 2; q.KB1 = 0; q.planes = planes; q.epi = TC_EPI_LN; q.bias = b4; q.nres = N; q.res_mask = res_mask;
   q.ln_g = ln_g; q.ln_b = ln_b; q.out_hi = w.z_hi; q.out_lo = w.z_lo;
+  q.wb = next_wb; q.wb_bias = next_bb; q.pbias = w.pbias;
   if (tc_launch(w.m_e1_h, w.m_e1_l, w.m_e1_h, w.m_e1_l, tw.ee4, q, st, launches)) return -2;
   return 0;
 }
@@ -1107,7 +1172,8 @@ inline int tc_edge_embed(const TcWeights& tw, TcWorkspace& w, int prec, const fl
 // EdgeTransition (model/ipa_pytorch.py:218-233) with the separable first/last layers (node terms P,Q,U,V precomputed):
 //   h1 = relu(z·W1z^T + P_i + Q_j);  h2 = relu(h1·W2^T + b2);  z' = LN([h2|z]·[Wf|Wfz]^T + U_i + V_j)·mask
 inline int tc_edge_transition(const TcWeights& tw, TcWorkspace& w, int blk, int prec, const float* pquv, const float* b2, const float* ln_g,
-                              const float* ln_b, const float* res_mask, int B, int N, cudaStream_t st, long long* launches) {
+                              const float* ln_b, const float* res_mask, const float* next_wb, const float* next_bb, int B, int N,
+                              cudaStream_t st, long long* launches) {
   const long long E = w.E;
   const int planes = prec == 1 ? 2 : 1;
   if (E > 0x7fffffffLL) return -1;
@@ -1115,6 +1181,7 @@ inline int tc_edge_transition(const TcWeights& tw, TcWorkspace& w, int blk, int 
     FusedParams f{};
     f.E = (int)E; f.planes = planes; f.nres = N; f.num_tiles = (int)((E + TC_BM - 1) / TC_BM);
     f.pquv = pquv; f.b2 = b2; f.ln_g = ln_g; f.ln_b = ln_b; f.res_mask = res_mask; f.out_hi = w.z_hi; f.out_lo = w.z_lo;
+    f.wb = next_wb; f.wb_bias = next_bb; f.pbias = w.pbias;
     f.prof = g_tc_prof;
     f.dbg_noq = getenv("FD_FU_NOQ") ? 1 : 0;
     const int grid = f.num_tiles < g_tc_sms ? f.num_tiles : g_tc_sms;
@@ -1135,6 +1202,7 @@ inline int tc_edge_transition(const TcWeights& tw, TcWorkspace& w, int blk, int 
   r.M = (int)E; r.N = C_Z; r.KB0 = 6; r.KB1 = 2; r.planes = planes; r.epi = TC_EPI_LN; r.rowadd = pquv; r.off_i = 2 * ET_HID;
   r.off_j = 2 * ET_HID + C_Z; r.ld_rowadd = ET_NODE; r.nres = N; r.res_mask = res_mask; r.ln_g = ln_g; r.ln_b = ln_b;
   r.out_hi = w.z_hi; r.out_lo = w.z_lo;
+  r.wb = next_wb; r.wb_bias = next_bb; r.pbias = w.pbias;
   if (tc_launch(w.m_h2_h, w.m_h2_l, w.m_z_h, w.m_z_l, tw.wf[blk], r, st, launches)) return -2;
   return 0;
 }
@@ -1168,13 +1236,14 @@ inline void tc_export_z(TcWorkspace& w, float* z_f32, int prec, cudaStream_t st)
   planes_to_f32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(w.z_hi, prec == 1 ? w.z_lo : nullptr, z_f32, n);
 }
 
-inline int tc_ipa_edge(TcWorkspace& w, float* L, const float* qp, const float* kp, const float* res_mask, const float* Wb, const float* bb,
-                       const float* gamma, const float* WdT, const float* bd, float* feats, int B, int N, int Np, int prec,
-                       cudaStream_t st, long long* launches) {
-  const size_t smem = (size_t)(H * Np + H * PQ * 3 + 2 * H * C_Z) * sizeof(float);
+// IPA edge pass in the tensor-core modes: the pair bias [E,8] was emitted by the LayerNorm epilogue of the kernel that produced
+// z (edge embedder for block 0, fused EdgeTransition afterwards), so z is streamed exactly once here.
+inline int tc_ipa_edge(TcWorkspace& w, float* L, const float* qp, const float* kp, const float* res_mask, const float* gamma,
+                       const float* WdT, const float* bd, float* feats, int B, int N, int Np, int prec, cudaStream_t st, long long* launches) {
+  const size_t smem = (size_t)(H * Np + 8 * H * C_Z) * sizeof(float);
   ZRef z; z.hi = w.z_hi; z.lo = w.z_lo;
-  if (prec == 1) ipa_edge_kernel<2><<<dim3(N, B), 256, smem, st>>>(z, L, qp, kp, res_mask, Wb, bb, gamma, WdT, bd, feats, N, Np);
-  else ipa_edge_kernel<1><<<dim3(N, B), 256, smem, st>>>(z, L, qp, kp, res_mask, Wb, bb, gamma, WdT, bd, feats, N, Np);
+  if (prec == 1) ipa_edge2_kernel<2><<<dim3(N, B), 256, smem, st>>>(z, L, w.pbias, qp, kp, res_mask, gamma, WdT, bd, feats, N, Np);
+  else ipa_edge2_kernel<1><<<dim3(N, B), 256, smem, st>>>(z, L, w.pbias, qp, kp, res_mask, gamma, WdT, bd, feats, N, Np);
   if (launches) ++*launches;
   return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
