@@ -619,7 +619,7 @@ static int forward_impl(fd_context* h, int B, int N, const float* rigids_t, cons
     if (!f.err) {
       const size_t smem = (size_t)(H * Np + H * PQ * 3 + 2 * H * C_Z) * sizeof(float);
       if (tc) {
-        if (tc_ipa_edge(w.tc, w.L, w.qp, w.kp, res_mask, X.gamma, X.WdT, X.bd, w.feats, B, N, Np, h->precision, st, &h->launches))
+        if (tc_ipa_edge(h->tcw, w.tc, b, w.L, w.qp, w.kp, res_mask, X.bb, X.gamma, X.WdT, X.bd, w.feats, B, N, Np, h->precision, st, &h->launches))
           f.err = fail(FD_ECUDA, "ipa_edge (planes) launch failed: %s", cudaGetErrorString(cudaGetLastError()));
       } else {
         ZRef zr; zr.f32 = w.z;

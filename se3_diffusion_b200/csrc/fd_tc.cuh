@@ -74,6 +74,12 @@ __device__ __forceinline__ void split2_bf16(float v0, float v1, uint32_t& hi, ui
   const __nv_bfloat162 l = __floats2bfloat162_rn(r0, r1);
   lo = *reinterpret_cast<const uint32_t*>(&l);
 }
+// 256-bit read-only global load (LDG.E.256): halves the LSU instruction / wavefront count of per-row scattered reads
+__device__ __forceinline__ void ldg256(const float* p, float (&v)[8]) {
+  asm volatile("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+               : "l"(p));
+}
 // one elected lane of a converged warp (CUTLASS elect_one_sync): operands stay warp-uniform, only the issue is predicated
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
@@ -135,6 +141,16 @@ __device__ __forceinline__ void umma_kstep(uint32_t d, uint64_t aH, uint64_t aL,
   }
 }
 
+// optional 4th term lo·lo (used by the small pair-bias GEMM, where MMA time is free and the logits want the extra bits)
+__device__ __forceinline__ void umma_lolo(uint32_t d, uint64_t aL, uint64_t bL, uint32_t idesc) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "setp.eq.b32 q, 0, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, q;\n\t}" ::"r"(d),
+      "l"(aL), "l"(bL), "r"(idesc)
+      : "memory");
+}
+
 // K-major, 128B-swizzled smem operand descriptor (rows of 64 bf16 = 128 B, 8-row swizzle atoms of 1024 B)
 __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
   uint64_t d = 0;
@@ -180,7 +196,9 @@ struct TcGemmParams {
   const float* residual; int ldr;
   const float* rowmask;     // [M]
   int relu;
-  const float* wb; const float* wb_bias; float* pbias;   // LN epilogue only: next IPA block's linear_b -> pair bias [M,8]
+  const float* wb; const float* wb_bias; float* pbias;   // LN epilogue only: next IPA block's linear_b -> pair bias [M,8] (unused now)
+  int lolo;                 // also accumulate a_lo·b_lo (4-term product)
+  int mma_n;                // UMMA N (128, or 16 for the 8-wide pair-bias GEMM: only the first rows of the weight tile are multiplied)
 };
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -267,7 +285,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mA0h, const __grid_constant__
   } else if (warp == 1) {
     // ================================ MMA issuer ================================
     {
-      const uint32_t idesc = make_idesc_bf16(TC_BM, TC_NC);
+      const uint32_t idesc = make_idesc_bf16(TC_BM, p.mma_n);
       uint32_t ia = 0, ib = 0, it = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
         mbar_wait(tmem_empty, (it & 1u) ^ 1u);      // epilogue has drained the previous tile's accumulators
@@ -286,8 +304,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mA0h, const __grid_constant__
             const uint64_t dAH = make_sw128_desc(aH), dAL = make_sw128_desc(aL), dBH = make_sw128_desc(bH), dBL = make_sw128_desc(bL);
             if (elect_one()) {
 #pragma unroll
-              for (int ks = 0; ks < TC_BK / 16; ++ks)   // 16 bf16 = 32 bytes along K inside the swizzle atom: descriptor += 2
+              for (int ks = 0; ks < TC_BK / 16; ++ks) {  // 16 bf16 = 32 bytes along K inside the swizzle atom: descriptor += 2
                 umma_kstep(d, dAH + 2u * ks, dAL + 2u * ks, dBH + 2u * ks, dBL + 2u * ks, idesc, (kb > 0 || ks > 0) ? 1u : 0u, p.planes == 2);
+                if (p.lolo && p.planes == 2) umma_lolo(d, dAL + 2u * ks, dBL + 2u * ks, idesc);
+              }
               tc_commit(b_empty(sb));     // frees this weight stage once the MMAs above retire
             }
             __syncwarp();
@@ -326,7 +346,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mA0h, const __grid_constant__
       const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16);
       if (p.epi == TC_EPI_F32) {
         const float rm = (valid && p.rowmask) ? p.rowmask[m] : 1.f;
-        for (int c0 = 0; c0 < NCH * TC_NC; c0 += 32) {
+        const int ncols = min(NCH * TC_NC, ((p.n_valid - n0 + 31) / 32) * 32);     // skip accumulator columns beyond the valid width
+        for (int c0 = 0; c0 < ncols; c0 += 32) {
           uint32_t r[32];
           tmem_ld32(trow + (uint32_t)c0, r);
           const int n = n0 + c0;
@@ -768,9 +789,11 @@ tc_edge_fused_kernel(const __grid_constant__ CUtensorMap mZh, const __grid_const
         float v[64];
         const int col0 = c * 64;
 #pragma unroll
-        for (int q = 0; q < 16; ++q) {
-          const float4 y4 = valid ? __ldg(reinterpret_cast<const float4*>(pQ + col0 + q * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
-          v[q * 4 + 0] = y4.x; v[q * 4 + 1] = y4.y; v[q * 4 + 2] = y4.z; v[q * 4 + 3] = y4.w;
+        for (int q = 0; q < 8; ++q) {
+          float y8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+          if (valid) ldg256(pQ + col0 + q * 8, y8);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[q * 8 + e] = y8[e];
         }
         FU_PROF(c_t1f, mbar_wait(t1_full(grp), n_t1f & 1u)); ++n_t1f;
         tc_fence_after();
@@ -832,10 +855,12 @@ tc_edge_fused_kernel(const __grid_constant__ CUtensorMap mZh, const __grid_const
           const float* pU = pP + 2 * ET_HID + cb;
           const float* pV = pQ + (ET_HID + C_Z) + cb;   // pQ points at +384: V sits at 896 = 384 + 512
 #pragma unroll
-          for (int q = 0; q < 16; ++q) {
-            const float4 x4 = __ldg(reinterpret_cast<const float4*>(pU + q * 4));
-            const float4 y4 = __ldg(reinterpret_cast<const float4*>(pV + q * 4));
-            v[q * 4 + 0] = x4.x + y4.x; v[q * 4 + 1] = x4.y + y4.y; v[q * 4 + 2] = x4.z + y4.z; v[q * 4 + 3] = x4.w + y4.w;
+          for (int q = 0; q < 8; ++q) {
+            float x8[8], y8[8];
+            ldg256(pU + q * 8, x8);
+            ldg256(pV + q * 8, y8);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[q * 8 + e] = x8[e] + y8[e];
           }
         } else {
 #pragma unroll
@@ -1012,6 +1037,7 @@ struct TcWeights {
   std::map<const float*, TcMat> lin;   // node-path linears, keyed by the fp32 device weight pointer (rows padded to 128)
   TcMat ee2, ee4;                 // edge embedder layers 2 and 4: [128][128]
   TcMat w1z[3], w2[3], wf[3];     // EdgeTransition: [384][128], [384][384], [128][512] = [Wf | Wf[:, :128]]
+  TcMat wb[4];                    // IPA linear_b padded to [128][128] (rows 0..7 real): pair bias z·Wb^T on the tensor cores (UMMA N = 16)
 };
 
 struct TcWorkspace {
@@ -1054,6 +1080,12 @@ inline int tc_pack_weights(TcWeights& tw, const std::map<std::string, const floa
   auto add = [&](TcMat* m, const float* src, int rows, int cols) { items.push_back({m, std::vector<float>(src, src + (size_t)rows * cols), rows, cols}); };
   add(&tw.ee2, M.at("embedding_layer.edge_embedder.2.weight"), 128, 128);
   add(&tw.ee4, M.at("embedding_layer.edge_embedder.4.weight"), 128, 128);
+  for (int b = 0; b < 4; ++b) {
+    const float* wbp = M.at("score_model.trunk.ipa_" + std::to_string(b) + ".linear_b.weight");   // [8][128]
+    std::vector<float> w((size_t)128 * C_Z, 0.f);
+    memcpy(w.data(), wbp, (size_t)H * C_Z * sizeof(float));
+    items.push_back({&tw.wb[b], std::move(w), 128, C_Z});
+  }
   for (int b = 0; b < 3; ++b) {
     const std::string p = "score_model.trunk.edge_transition_" + std::to_string(b) + ".";
     const float* w1 = M.at(p + "trunk.0.weight");      // [384][384]
@@ -1140,6 +1172,7 @@ inline int tc_launch(const CUtensorMap& a0h, const CUtensorMap& a0l, const CUten
   if (p.epi != TC_EPI_F32) {
     p.m_tiles = (p.M + TC_BM - 1) / TC_BM; p.nch = p.N / TC_NC; p.num_tiles = p.m_tiles; p.n_valid = p.N;
   }
+  if (p.mma_n == 0) p.mma_n = TC_NC;
   const int grid = p.num_tiles < g_tc_sms ? p.num_tiles : g_tc_sms;
   tc_gemm_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(a0h, a0l, a1h, a1l, Wt.mh, Wt.ml, p);
   if (launches) ++*launches;
@@ -1164,7 +1197,7 @@ inline int tc_edge_embed(const TcWeights& tw, TcWorkspace& w, int prec, const fl
   TcGemmParams q{};
   q.M = (int)E; q.N = 128; q.KB0 = 2; q.KB1 = 0; q.planes = planes; q.epi = TC_EPI_LN; q.bias = b4; q.nres = N; q.res_mask = res_mask;
   q.ln_g = ln_g; q.ln_b = ln_b; q.out_hi = w.z_hi; q.out_lo = w.z_lo;
-  q.wb = next_wb; q.wb_bias = next_bb; q.pbias = w.pbias;
+  (void)next_wb; (void)next_bb;   // pair bias now comes from tc_ipa_edge's own N=16 GEMM over the z planes
   if (tc_launch(w.m_e1_h, w.m_e1_l, w.m_e1_h, w.m_e1_l, tw.ee4, q, st, launches)) return -2;
   return 0;
 }
@@ -1181,7 +1214,7 @@ inline int tc_edge_transition(const TcWeights& tw, TcWorkspace& w, int blk, int 
     FusedParams f{};
     f.E = (int)E; f.planes = planes; f.nres = N; f.num_tiles = (int)((E + TC_BM - 1) / TC_BM);
     f.pquv = pquv; f.b2 = b2; f.ln_g = ln_g; f.ln_b = ln_b; f.res_mask = res_mask; f.out_hi = w.z_hi; f.out_lo = w.z_lo;
-    f.wb = next_wb; f.wb_bias = next_bb; f.pbias = w.pbias;
+    (void)next_wb; (void)next_bb;
     f.prof = g_tc_prof;
     f.dbg_noq = getenv("FD_FU_NOQ") ? 1 : 0;
     const int grid = f.num_tiles < g_tc_sms ? f.num_tiles : g_tc_sms;
@@ -1202,7 +1235,7 @@ inline int tc_edge_transition(const TcWeights& tw, TcWorkspace& w, int blk, int 
   r.M = (int)E; r.N = C_Z; r.KB0 = 6; r.KB1 = 2; r.planes = planes; r.epi = TC_EPI_LN; r.rowadd = pquv; r.off_i = 2 * ET_HID;
   r.off_j = 2 * ET_HID + C_Z; r.ld_rowadd = ET_NODE; r.nres = N; r.res_mask = res_mask; r.ln_g = ln_g; r.ln_b = ln_b;
   r.out_hi = w.z_hi; r.out_lo = w.z_lo;
-  r.wb = next_wb; r.wb_bias = next_bb; r.pbias = w.pbias;
+
   if (tc_launch(w.m_h2_h, w.m_h2_l, w.m_z_h, w.m_z_l, tw.wf[blk], r, st, launches)) return -2;
   return 0;
 }
@@ -1236,10 +1269,16 @@ inline void tc_export_z(TcWorkspace& w, float* z_f32, int prec, cudaStream_t st)
   planes_to_f32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(w.z_hi, prec == 1 ? w.z_lo : nullptr, z_f32, n);
 }
 
-// IPA edge pass in the tensor-core modes: the pair bias [E,8] was emitted by the LayerNorm epilogue of the kernel that produced
-// z (edge embedder for block 0, fused EdgeTransition afterwards), so z is streamed exactly once here.
-inline int tc_ipa_edge(TcWorkspace& w, float* L, const float* qp, const float* kp, const float* res_mask, const float* gamma,
-                       const float* WdT, const float* bd, float* feats, int B, int N, int Np, int prec, cudaStream_t st, long long* launches) {
+// IPA edge pass in the tensor-core modes.  Pair bias  pbias[e,h] = z_e·Wb[h]^T + bb[h]  first, as a memory-bound tcgen05 GEMM over
+// the z planes (UMMA N = 16, 8 valid columns, fp32 out), then the attention kernel streams z exactly once (Σ_j a·z).
+inline int tc_ipa_edge(const TcWeights& tw, TcWorkspace& w, int blk, float* L, const float* qp, const float* kp, const float* res_mask,
+                       const float* bb, const float* gamma, const float* WdT, const float* bd, float* feats, int B, int N, int Np, int prec,
+                       cudaStream_t st, long long* launches) {
+  const int planes = prec == 1 ? 2 : 1;
+  TcGemmParams p{};
+  p.M = (int)w.E; p.N = 128; p.KB0 = 2; p.KB1 = 0; p.planes = planes; p.epi = TC_EPI_F32; p.bias = bb; p.mma_n = 16; p.lolo = 1;
+  p.m_tiles = (int)((w.E + TC_BM - 1) / TC_BM); p.nch = 1; p.num_tiles = p.m_tiles; p.n_valid = H; p.out_f32 = w.pbias; p.ldo = H;
+  if (tc_launch(w.m_z_h, w.m_z_l, w.m_z_h, w.m_z_l, tw.wb[blk], p, st, launches)) return -2;
   const size_t smem = (size_t)(H * Np + 8 * H * C_Z) * sizeof(float);
   ZRef z; z.hi = w.z_hi; z.lo = w.z_lo;
   if (prec == 1) ipa_edge2_kernel<2><<<dim3(N, B), 256, smem, st>>>(z, L, w.pbias, qp, kp, res_mask, gamma, WdT, bd, feats, N, Np);
