@@ -549,6 +549,28 @@ __device__ __forceinline__ void umma_kstep_ts(uint32_t d, uint32_t aH, uint32_t 
   }
 }
 
+// Warp-cooperative store of a [32 rows x 64 bf16] block held one row per lane (w = the row's 32 packed words) through a 4 KB
+// XOR-swizzled shared-memory staging buffer: every global store instruction then writes four full 128-byte row segments
+// instead of 32 scattered 16-byte pieces (8x fewer LSU wavefronts; the LayerNorm epilogues were bound by them).
+__device__ __forceinline__ void warp_store_rows64(uint32_t stage, const uint32_t (&w)[32], __nv_bfloat16* out, long long m_warp, int col0,
+                                                  long long E, int lane) {
+#pragma unroll
+  for (int u = 0; u < 8; ++u)
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage + (uint32_t)(lane * 128 + ((u ^ (lane & 7)) << 4))), "r"(w[4 * u]),
+                 "r"(w[4 * u + 1]), "r"(w[4 * u + 2]), "r"(w[4 * u + 3])
+                 : "memory");
+  __syncwarp();
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int r = k * 4 + (lane >> 3), u = lane & 7;
+    uint4 val;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(val.x), "=r"(val.y), "=r"(val.z), "=r"(val.w)
+                 : "r"(stage + (uint32_t)(r * 128 + ((u ^ (r & 7)) << 4))) : "memory");
+    if (m_warp + r < E) *reinterpret_cast<uint4*>(out + (m_warp + r) * 128 + col0 + u * 8) = val;
+  }
+  __syncwarp();
+}
+
 // Weight-ring helpers as force-inlined members (warp-uniform: the whole warp runs them, one elected lane issues)
 struct FuRing {
   uint32_t ringb, bar0, slot_bytes, S, planes;
@@ -606,7 +628,7 @@ struct FuRing {
 
 constexpr int FU_THREADS = 320;   // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two groups of four)
 constexpr int FU_RING_BYTES = 128 * 1024;
-constexpr size_t FU_SMEM_BYTES = 64 * 1024 + FU_RING_BYTES + 512 + 2048 + 4096 + 8192;   // + Wb [8][128] + pair-bias partials [2][128][8]   // dynamic smem starts 1024-aligned (no static smem here)
+constexpr size_t FU_SMEM_BYTES = 64 * 1024 + FU_RING_BYTES + 512 + 2048 + 8 * 4096;   // + LayerNorm statistics + 8 x 4 KB store staging   // dynamic smem starts 1024-aligned (no static smem here)
 
 struct FusedParams {
   int E, planes, nres, num_tiles;
@@ -645,8 +667,6 @@ tc_edge_fused_kernel(const __grid_constant__ CUtensorMap mZh, const __grid_const
   auto a2_full = [&](int c) { return bar0 + 8u * (29 + c); };      // one per h2 chunk (no back-pressure on epi2: avoid 2-phase run-ahead)
   const uint32_t tmem_ptr_addr = bar0 + 8u * 35;
   const uint32_t stats = bar0 + 512u;     // LayerNorm partial statistics [2][128 rows][2] fp32 = 2 KB
-  const uint32_t wb_s = stats + 2048u;    // linear_b weights [8][128] fp32
-  const uint32_t pb_s = wb_s + 4096u;     // pair-bias partials [2 halves][128 rows][8] fp32
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // warp-uniform by construction
   if (threadIdx.x == 0) {
@@ -662,9 +682,6 @@ tc_edge_fused_kernel(const __grid_constant__ CUtensorMap mZh, const __grid_const
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_ptr_addr), "r"(TC_TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  if (p.pbias && threadIdx.x >= 64) {
-    for (int i = threadIdx.x - 64; i < H * C_Z; i += FU_THREADS - 64) asm volatile("st.shared.f32 [%0], %1;" ::"r"(wb_s + 4u * i), "f"(p.wb[i]) : "memory");
   }
   tc_fence_before();
   __syncthreads();
@@ -903,56 +920,273 @@ tc_edge_fused_kernel(const __grid_constant__ CUtensorMap mZh, const __grid_const
         float ovar;
         asm volatile("ld.shared.f32 %0, [%1];" : "=f"(ovar) : "r"(st_other + 4) : "memory");
         const float rstd = rsqrtf((pvar + ovar) * (1.f / 128.f) + 1e-5f);
-        float pb[H];
-#pragma unroll
-        for (int hh = 0; hh < H; ++hh) pb[hh] = 0.f;
-        if (valid) {
+        {
+          uint32_t hw[32], lw[32];
 #pragma unroll
           for (int c0 = 0; c0 < 64; c0 += 8) {
             const float4 g0 = __ldg(reinterpret_cast<const float4*>(p.ln_g + cb + c0)), g1v = __ldg(reinterpret_cast<const float4*>(p.ln_g + cb + c0 + 4));
             const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.ln_b + cb + c0)), b1v = __ldg(reinterpret_cast<const float4*>(p.ln_b + cb + c0 + 4));
             const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1v.x, g1v.y, g1v.z, g1v.w};
             const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1v.x, b1v.y, b1v.z, b1v.w};
-            float y[8];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) y[e] = ((v[c0 + e] - mean) * rstd * gg[e] + bb[e]) * emask;
-            uint32_t h[4], l[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) split2_bf16(y[2 * e], y[2 * e + 1], h[e], l[e]);
-            *reinterpret_cast<uint4*>(p.out_hi + m * 128 + cb + c0) = make_uint4(h[0], h[1], h[2], h[3]);
-            if (p.planes == 2) *reinterpret_cast<uint4*>(p.out_lo + m * 128 + cb + c0) = make_uint4(l[0], l[1], l[2], l[3]);
-            if (p.pbias) {     // next IPA block's pair bias: partial dots of this thread's 64 channels with linear_b (smem, broadcast reads)
-#pragma unroll
-              for (int hh = 0; hh < H; ++hh) {
-                float w0, w1, w2, w3, w4, w5, w6, w7;
-                const uint32_t wa = wb_s + 4u * (uint32_t)(hh * C_Z + cb + c0);
-                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(w0), "=f"(w1), "=f"(w2), "=f"(w3) : "r"(wa));
-                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(w4), "=f"(w5), "=f"(w6), "=f"(w7) : "r"(wa + 16u));
-                pb[hh] += (y[0] * w0 + y[1] * w1) + (y[2] * w2 + y[3] * w3) + (y[4] * w4 + y[5] * w5) + (y[6] * w6 + y[7] * w7);
-              }
-            }
+            for (int e = 0; e < 4; ++e)
+              split2_bf16(((v[c0 + 2 * e] - mean) * rstd * gg[2 * e] + bb[2 * e]) * emask,
+                          ((v[c0 + 2 * e + 1] - mean) * rstd * gg[2 * e + 1] + bb[2 * e + 1]) * emask, hw[c0 / 2 + e], lw[c0 / 2 + e]);
           }
-        }
-        if (p.pbias) {       // the two column halves of a row meet in smem; group 0 writes the row's 8 biases
-          const uint32_t pm = pb_s + (uint32_t)((grp * 128 + row) * 32);
-          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(pm), "f"(pb[0]), "f"(pb[1]), "f"(pb[2]), "f"(pb[3]) : "memory");
-          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(pm + 16u), "f"(pb[4]), "f"(pb[5]), "f"(pb[6]), "f"(pb[7]) : "memory");
-          asm volatile("bar.sync %0, 64;" ::"r"(2 + quad) : "memory");
-          if (grp == 0 && valid) {
-            const uint32_t po = pb_s + (uint32_t)((128 + row) * 32);
-            float o0, o1, o2, o3, o4, o5, o6, o7;
-            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(o0), "=f"(o1), "=f"(o2), "=f"(o3) : "r"(po));
-            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(o4), "=f"(o5), "=f"(o6), "=f"(o7) : "r"(po + 16u));
-            const float4 bA = __ldg(reinterpret_cast<const float4*>(p.wb_bias)), bB = __ldg(reinterpret_cast<const float4*>(p.wb_bias + 4));
-            *reinterpret_cast<float4*>(p.pbias + m * H) = make_float4(pb[0] + o0 + bA.x, pb[1] + o1 + bA.y, pb[2] + o2 + bA.z, pb[3] + o3 + bA.w);
-            *reinterpret_cast<float4*>(p.pbias + m * H + 4) = make_float4(pb[4] + o4 + bB.x, pb[5] + o5 + bB.y, pb[6] + o6 + bB.z, pb[7] + o7 + bB.w);
-          }
-          asm volatile("bar.sync %0, 64;" ::"r"(2 + quad) : "memory");   // partial slots are reused by the next tile
+          const long long m_warp = m - lane;
+          const uint32_t stage = stats + 2048u + (uint32_t)(warp - 2) * 4096u;
+          warp_store_rows64(stage, hw, p.out_hi, m_warp, cb, p.E, lane);
+          if (p.planes == 2) warp_store_rows64(stage, lw, p.out_lo, m_warp, cb, p.E, lane);
         }
         if (prof_on) c_ln += clock64() - c_ln0;
       }
     }
     if (prof_on && lane == 0) { p.prof[16] = clock64() - c_start; p.prof[17] = c_t1f; p.prof[19] = c_h2f; p.prof[20] = c_yf; p.prof[21] = c_ln; }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TC_TMEM_COLS) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Fused edge-embedder tail (model/score_network.py:64-72 edge_embedder layers 2..4):
+//     z = LayerNorm(relu(h0·W2^T + b2)·W4^T + b4) · mask        per 128-edge tile, h1 never leaves the SM.
+//   Both weight matrices (hi/lo, 128 KB) stay resident in shared memory for the whole persistent CTA; the only stream is the
+//   h0 tile (TMA, 64 KB).  TMEM is split in two 256-column halves used by alternating tiles: H1 (128 fp32 columns, rewritten
+//   in place as the bf16 hi/lo A image of the second GEMM) | Y (128 fp32 columns).  The MMA warp issues the first GEMM of
+//   tile t+1 before the second GEMM of tile t, so the tensor pipe works under the epilogue of the previous tile.
+//   warps: 0 = TMA producer, 1 = MMA issuer (+TMEM alloc), 2..9 = epilogue (quadrant = warp & 3, column half = (warp-2) >> 2).
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int EF_THREADS = 320;
+constexpr size_t EF_SMEM_BYTES = 12 * (size_t)TC_PLANE_BYTES + 512 + 2048 + 8 * 4096;   // dynamic smem starts 1024-aligned (no static smem)
+
+struct EmbedFusedParams {
+  int E, planes, nres, num_tiles;
+  const float* b2; const float* b4; const float* ln_g; const float* ln_b; const float* res_mask;
+  __nv_bfloat16* out_hi; __nv_bfloat16* out_lo;
+};
+
+__global__ void __launch_bounds__(EF_THREADS, 1)
+tc_embed_fused_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ CUtensorMap mAl,
+                      const __grid_constant__ CUtensorMap mW2h, const __grid_constant__ CUtensorMap mW2l,
+                      const __grid_constant__ CUtensorMap mW4h, const __grid_constant__ CUtensorMap mW4l, const EmbedFusedParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  constexpr uint32_t PL = TC_PLANE_BYTES;   // 16 KB: 128 rows x 64 bf16
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  auto wbuf = [&](int l, int kb, int pl) { return base + (uint32_t)((l * 2 + kb) * 2 + pl) * PL; };
+  auto abuf = [&](int kb, int pl) { return base + 8u * PL + (uint32_t)(kb * 2 + pl) * PL; };
+  const uint32_t bar0 = base + 12u * PL;
+  const uint32_t w_full = bar0, a_full = bar0 + 8u, a_empty = bar0 + 16u;
+  auto h1_full = [&](uint32_t x) { return bar0 + 8u * (3 + x); };
+  auto c_full = [&](uint32_t x) { return bar0 + 8u * (5 + x); };
+  auto y_full = [&](uint32_t x) { return bar0 + 8u * (7 + x); };
+  auto t_empty = [&](uint32_t x) { return bar0 + 8u * (9 + x); };
+  const uint32_t tmem_ptr_addr = bar0 + 8u * 11;
+  const uint32_t stats = bar0 + 512u;     // LayerNorm partial statistics [2][128 rows][2] fp32 = 2 KB, then 8 x 4 KB store staging
+
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    mbar_init(w_full, 1); mbar_init(a_full, 1); mbar_init(a_empty, 1);
+    for (uint32_t x = 0; x < 2; ++x) { mbar_init(h1_full(x), 1); mbar_init(c_full(x), 8); mbar_init(y_full(x), 1); mbar_init(t_empty(x), 8); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    tma_prefetch_desc(&mAh); tma_prefetch_desc(&mW2h); tma_prefetch_desc(&mW4h);
+    if (p.planes == 2) { tma_prefetch_desc(&mAl); tma_prefetch_desc(&mW2l); tma_prefetch_desc(&mW4l); }
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_ptr_addr), "r"(TC_TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_addr));
+  const uint32_t n_my = blockIdx.x < (unsigned)p.num_tiles ? (uint32_t)((p.num_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1) : 0u;
+
+  if (warp == 0) {
+    // ============================================ TMA producer ============================================
+    if (elect_one()) {
+      mbar_expect_tx(w_full, (uint32_t)p.planes * 4 * PL);
+      for (int kb = 0; kb < 2; ++kb) {
+        tma_load_2d(wbuf(0, kb, 0), &mW2h, w_full, kb * 64, 0);
+        tma_load_2d(wbuf(1, kb, 0), &mW4h, w_full, kb * 64, 0);
+        if (p.planes == 2) {
+          tma_load_2d(wbuf(0, kb, 1), &mW2l, w_full, kb * 64, 0);
+          tma_load_2d(wbuf(1, kb, 1), &mW4l, w_full, kb * 64, 0);
+        }
+      }
+    }
+    __syncwarp();
+    for (uint32_t it = 0; it < n_my; ++it) {
+      const int m0 = ((int)blockIdx.x + (int)it * (int)gridDim.x) * TC_BM;
+      mbar_wait(a_empty, (it & 1u) ^ 1u);
+      if (elect_one()) {
+        mbar_expect_tx(a_full, (uint32_t)p.planes * 2 * PL);
+        for (int kb = 0; kb < 2; ++kb) {
+          tma_load_2d(abuf(kb, 0), &mAh, a_full, kb * 64, m0);
+          if (p.planes == 2) tma_load_2d(abuf(kb, 1), &mAl, a_full, kb * 64, m0);
+        }
+      }
+      __syncwarp();
+    }
+  } else if (warp == 1) {
+    // ============================================ MMA issuer ============================================
+    const uint32_t idesc = make_idesc_bf16(TC_BM, 128);
+    const bool x3 = p.planes == 2;
+    mbar_wait(w_full, 0u);
+    tc_fence_after();
+    // first GEMM of tile k: H1[k&1] = h0 · W2^T (A and B from shared memory)
+    auto g1 = [&](uint32_t k) {
+      const uint32_t x = k & 1u;
+      mbar_wait(t_empty(x), ((k >> 1) & 1u) ^ 1u);     // tile k-2 (same TMEM half) fully read by its LayerNorm
+      mbar_wait(a_full, k & 1u);
+      tc_fence_after();
+      if (elect_one()) {
+        for (int kb = 0; kb < 2; ++kb) {
+          const uint64_t dAH = make_sw128_desc(abuf(kb, 0)), dAL = make_sw128_desc(abuf(kb, 1));
+          const uint64_t dBH = make_sw128_desc(wbuf(0, kb, 0)), dBL = make_sw128_desc(wbuf(0, kb, 1));
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks)
+            umma_kstep(tmem_base + 256u * x, dAH + 2u * ks, dAL + 2u * ks, dBH + 2u * ks, dBL + 2u * ks, idesc, (kb == 0 && ks == 0) ? 0u : 1u, x3);
+        }
+        tc_commit(a_empty);
+        tc_commit(h1_full(x));
+      }
+      __syncwarp();
+    };
+    if (n_my > 0) g1(0);
+    for (uint32_t it = 0; it < n_my; ++it) {
+      if (it + 1 < n_my) g1(it + 1);
+      const uint32_t x = it & 1u;
+      mbar_wait(c_full(x), (it >> 1) & 1u);              // epilogue wrote relu(h1) as bf16 hi/lo images over H1[x]
+      tc_fence_after();
+      if (elect_one()) {
+        for (int c = 0; c < 2; ++c) {
+          const uint32_t a = tmem_base + 256u * x + 64u * c;
+          const uint64_t dBH = make_sw128_desc(wbuf(1, c, 0)), dBL = make_sw128_desc(wbuf(1, c, 1));
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks)
+            umma_kstep_ts(tmem_base + 256u * x + 128u, a + 8u * ks, a + 32u + 8u * ks, dBH + 2u * ks, dBL + 2u * ks, idesc, (c == 0 && ks == 0) ? 0u : 1u, x3);
+        }
+        tc_commit(y_full(x));
+      }
+      __syncwarp();
+    }
+  } else {
+    // ============================================ epilogue warps 2..9 ============================================
+    const int quad = warp & 3, half = (warp - 2) >> 2;
+    const int row = quad * 32 + lane;
+    const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16);
+    const int cb = half * 64;
+    const uint32_t stage = stats + 2048u + (uint32_t)(warp - 2) * 4096u;     // this warp's store-staging buffer
+    for (uint32_t it = 0; it < n_my; ++it) {
+      const uint32_t x = it & 1u, ph = (it >> 1) & 1u;
+      const long long m = (long long)((int)blockIdx.x + (int)it * (int)gridDim.x) * TC_BM + row;
+      const bool valid = m < p.E;
+      float emask = 0.f;
+      if (valid) {
+        const long long nn = (long long)p.nres * p.nres;
+        const long long b = m / nn;
+        const int rem = (int)(m - b * nn);
+        const int ri = rem / p.nres, rj = rem - ri * p.nres;
+        emask = p.res_mask[b * p.nres + ri] * p.res_mask[b * p.nres + rj];
+      }
+      // ---- relu(H1 + b2) -> bf16 hi/lo A image over this warp's own 64 columns (hi words [0,32), lo words [32,64)) ----
+      mbar_wait(h1_full(x), ph);
+      tc_fence_after();
+      {
+        const uint32_t tchunk = trow + 256u * x + (uint32_t)cb;
+        uint32_t r0[32], r1[32];
+        tmem_ld32_nowait(tchunk, r0);
+        tmem_ld32_nowait(tchunk + 32u, r1);
+        tmem_ld_wait();
+        uint32_t h[16], l[16];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float4 ba = __ldg(reinterpret_cast<const float4*>(p.b2 + cb + q * 4));
+          split2_bf16(fmaxf(__uint_as_float(r0[q * 4 + 0]) + ba.x, 0.f), fmaxf(__uint_as_float(r0[q * 4 + 1]) + ba.y, 0.f), h[2 * q], l[2 * q]);
+          split2_bf16(fmaxf(__uint_as_float(r0[q * 4 + 2]) + ba.z, 0.f), fmaxf(__uint_as_float(r0[q * 4 + 3]) + ba.w, 0.f), h[2 * q + 1], l[2 * q + 1]);
+        }
+        tmem_st16(tchunk, h);
+        if (p.planes == 2) tmem_st16(tchunk + 32u, l);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float4 bb = __ldg(reinterpret_cast<const float4*>(p.b2 + cb + 32 + q * 4));
+          split2_bf16(fmaxf(__uint_as_float(r1[q * 4 + 0]) + bb.x, 0.f), fmaxf(__uint_as_float(r1[q * 4 + 1]) + bb.y, 0.f), h[2 * q], l[2 * q]);
+          split2_bf16(fmaxf(__uint_as_float(r1[q * 4 + 2]) + bb.z, 0.f), fmaxf(__uint_as_float(r1[q * 4 + 3]) + bb.w, 0.f), h[2 * q + 1], l[2 * q + 1]);
+        }
+        tmem_st16(tchunk + 16u, h);
+        if (p.planes == 2) tmem_st16(tchunk + 48u, l);
+        tmem_st_wait();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(c_full(x));
+      // ---- LayerNorm(Y + b4) * mask -> z planes.  Two warps per quadrant split the 128 columns; partial statistics meet in smem ----
+      float v[64];
+      mbar_wait(y_full(x), ph);
+      tc_fence_after();
+      {
+        uint32_t r0[32], r1[32];
+        tmem_ld32_nowait(trow + 256u * x + 128u + (uint32_t)cb, r0);
+        tmem_ld32_nowait(trow + 256u * x + 128u + (uint32_t)(cb + 32), r1);
+        tmem_ld_wait();
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float4 ba = __ldg(reinterpret_cast<const float4*>(p.b4 + cb + q * 4)), bb = __ldg(reinterpret_cast<const float4*>(p.b4 + cb + 32 + q * 4));
+          v[q * 4 + 0] = __uint_as_float(r0[q * 4 + 0]) + ba.x; v[q * 4 + 1] = __uint_as_float(r0[q * 4 + 1]) + ba.y;
+          v[q * 4 + 2] = __uint_as_float(r0[q * 4 + 2]) + ba.z; v[q * 4 + 3] = __uint_as_float(r0[q * 4 + 3]) + ba.w;
+          v[32 + q * 4 + 0] = __uint_as_float(r1[q * 4 + 0]) + bb.x; v[32 + q * 4 + 1] = __uint_as_float(r1[q * 4 + 1]) + bb.y;
+          v[32 + q * 4 + 2] = __uint_as_float(r1[q * 4 + 2]) + bb.z; v[32 + q * 4 + 3] = __uint_as_float(r1[q * 4 + 3]) + bb.w;
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(t_empty(x));            // this TMEM half may be overwritten by tile it+2
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+      for (int q = 0; q < 64; q += 4) { s0 += v[q]; s1 += v[q + 1]; s2 += v[q + 2]; s3 += v[q + 3]; }
+      const float psum = (s0 + s1) + (s2 + s3);
+      const uint32_t st_mine = stats + (uint32_t)((half * 128 + row) * 8), st_other = stats + (uint32_t)(((half ^ 1) * 128 + row) * 8);
+      asm volatile("st.shared.f32 [%0], %1;" ::"r"(st_mine), "f"(psum) : "memory");
+      asm volatile("bar.sync %0, 64;" ::"r"(2 + quad) : "memory");
+      float osum;
+      asm volatile("ld.shared.f32 %0, [%1];" : "=f"(osum) : "r"(st_other) : "memory");
+      const float mean = (psum + osum) * (1.f / 128.f);
+      float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
+#pragma unroll
+      for (int q = 0; q < 64; q += 4) {
+        const float d0 = v[q] - mean, d1 = v[q + 1] - mean, d2 = v[q + 2] - mean, d3 = v[q + 3] - mean;
+        q0 = fmaf(d0, d0, q0); q1 = fmaf(d1, d1, q1); q2 = fmaf(d2, d2, q2); q3 = fmaf(d3, d3, q3);
+      }
+      const float pvar = (q0 + q1) + (q2 + q3);
+      asm volatile("st.shared.f32 [%0], %1;" ::"r"(st_mine + 4), "f"(pvar) : "memory");
+      asm volatile("bar.sync %0, 64;" ::"r"(2 + quad) : "memory");
+      float ovar;
+      asm volatile("ld.shared.f32 %0, [%1];" : "=f"(ovar) : "r"(st_other + 4) : "memory");
+      const float rstd = rsqrtf((pvar + ovar) * (1.f / 128.f) + 1e-5f);
+      {
+        uint32_t hw[32], lw[32];
+#pragma unroll
+        for (int c0 = 0; c0 < 64; c0 += 8) {
+          const float4 g0 = __ldg(reinterpret_cast<const float4*>(p.ln_g + cb + c0)), g1v = __ldg(reinterpret_cast<const float4*>(p.ln_g + cb + c0 + 4));
+          const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.ln_b + cb + c0)), b1v = __ldg(reinterpret_cast<const float4*>(p.ln_b + cb + c0 + 4));
+          const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1v.x, g1v.y, g1v.z, g1v.w};
+          const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1v.x, b1v.y, b1v.z, b1v.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            split2_bf16(((v[c0 + 2 * e] - mean) * rstd * gg[2 * e] + bb[2 * e]) * emask,
+                        ((v[c0 + 2 * e + 1] - mean) * rstd * gg[2 * e + 1] + bb[2 * e + 1]) * emask, hw[c0 / 2 + e], lw[c0 / 2 + e]);
+        }
+        const long long m_warp = m - lane;
+        warp_store_rows64(stage, hw, p.out_hi, m_warp, cb, p.E, lane);
+        if (p.planes == 2) warp_store_rows64(stage, lw, p.out_lo, m_warp, cb, p.E, lane);
+      }
+      // the stats slots are rewritten by this pair only after its next bar.sync pair, i.e. after both have read them
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -1007,6 +1241,7 @@ inline int tc_init(int sm_count) {
   g_encode = (PFN_encodeTiled)fn;
   if (cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES) != cudaSuccess) return -2;
   if (cudaFuncSetAttribute(tc_edge_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FU_SMEM_BYTES) != cudaSuccess) return -2;
+  if (cudaFuncSetAttribute(tc_embed_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EF_SMEM_BYTES) != cudaSuccess) return -2;
   if (cudaFuncSetAttribute(ipa_edge2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) return -2;
   if (cudaFuncSetAttribute(ipa_edge2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) return -2;
   return 0;
@@ -1190,6 +1425,16 @@ inline int tc_edge_embed(const TcWeights& tw, TcWorkspace& w, int prec, const fl
   if (planes == 2) edge_embed_l0_kernel<2><<<(unsigned)((E + 7) / 8), 256, 0, st>>>(AC, T, D, w0r, seq_idx, sc_ca, nullptr, w.h1_hi, w.h1_lo, 0, E, N);
   else edge_embed_l0_kernel<1><<<(unsigned)((E + 7) / 8), 256, 0, st>>>(AC, T, D, w0r, seq_idx, sc_ca, nullptr, w.h1_hi, w.h1_lo, 0, E, N);
   if (launches) ++*launches;
+  if (g_tc_fused) {   // layers 2..4 in one persistent kernel (h1 stays in tensor memory)
+    EmbedFusedParams f{};
+    f.E = (int)E; f.planes = planes; f.nres = N; f.num_tiles = (int)((E + TC_BM - 1) / TC_BM);
+    f.b2 = b2; f.b4 = b4; f.ln_g = ln_g; f.ln_b = ln_b; f.res_mask = res_mask; f.out_hi = w.z_hi; f.out_lo = w.z_lo;
+    (void)next_wb; (void)next_bb;
+    const int grid = f.num_tiles < g_tc_sms ? f.num_tiles : g_tc_sms;
+    tc_embed_fused_kernel<<<grid, EF_THREADS, EF_SMEM_BYTES, st>>>(w.m_e0_h, w.m_e0_l, tw.ee2.mh, tw.ee2.ml, tw.ee4.mh, tw.ee4.ml, f);
+    if (launches) ++*launches;
+    return cudaGetLastError() == cudaSuccess ? 0 : -2;
+  }
   TcGemmParams p{};
   p.M = (int)E; p.N = 128; p.KB0 = 2; p.KB1 = 0; p.planes = planes; p.epi = TC_EPI_RELU; p.bias = b2; p.nres = N;
   p.out_hi = w.h2_hi; p.out_lo = w.h2_lo;
