@@ -606,7 +606,10 @@ static int forward_impl(fd_context* h, int B, int N, const float* rigids_t, cons
     f.check("ipa_points");
     lc.end();
     lc.begin(ST_IPA_LOGITS);
-    {
+    if (tc) {
+      if (!f.err && tc_ipa_logits(w.tc, w.proj, w.L, B, N, Np, (float)sqrt(1.0 / (3 * C_HID)), st, &h->launches))
+        f.err = fail(FD_ECUDA, "ipa_logits (tensor-core) launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    } else {
       GemmArgs g;
       g.A = w.proj; g.lda = PROJ_ALL; g.sA0 = (long long)N * PROJ_ALL; g.sA1 = C_HID;
       g.B = w.proj + PROJ_Q; g.ldb = PROJ_ALL; g.sB0 = (long long)N * PROJ_ALL; g.sB1 = 2 * C_HID;
@@ -636,7 +639,12 @@ static int forward_impl(fd_context* h, int B, int N, const float* rigids_t, cons
       g.B = w.proj + PROJ_Q + C_HID; g.ldb = PROJ_ALL; g.sB0 = (long long)N * PROJ_ALL; g.sB1 = 2 * C_HID;
       g.C = w.feats; g.ldc = IPA_FEAT; g.sC0 = (long long)N * IPA_FEAT; g.sC1 = C_HID;
       g.M = N; g.N = C_HID; g.K = N; g.nb0 = B; g.nb1 = H;
-      f.gemm(g, false);
+      if (tc) {
+        if (!f.err && tc_ipa_av(w.tc, w.proj, w.L, w.feats, B, N, Np, st, &h->launches))
+          f.err = fail(FD_ECUDA, "ipa a.v (tensor-core) launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+      } else {
+        f.gemm(g, false);
+      }
       GemmArgs p = g;   // o_pt (global) = a · v_pts
       p.B = w.vp; p.ldb = H * PV * 3; p.sB0 = (long long)N * H * PV * 3; p.sB1 = PV * 3;
       p.C = w.optg; p.ldc = H * PV * 3; p.sC0 = (long long)N * H * PV * 3; p.sC1 = PV * 3; p.N = PV * 3;

@@ -199,6 +199,13 @@ struct TcGemmParams {
   const float* wb; const float* wb_bias; float* pbias;   // LN epilogue only: next IPA block's linear_b -> pair bias [M,8] (unused now)
   int lolo;                 // also accumulate a_lo·b_lo (4-term product)
   int mma_n;                // UMMA N (128, or 16 for the 8-wide pair-bias GEMM: only the first rows of the weight tile are multiplied)
+  // batched mode (attention GEMMs, TC_EPI_F32 only): tile -> (batch, local tile); batch -> (outer, inner) = (bat / bat_inner, bat % bat_inner).
+  // Both operands are activation planes addressed through 2-D maps with per-batch row / k offsets (TMA coordinates).
+  int bat_inner, bat_tiles;           // bat_inner == 0: unbatched
+  int a_row_s0, a_row_s1, a_k_s1;     // A coordinate offsets: row += outer*s0 + inner*s1, k += inner*k_s1
+  int b_row_s0, b_row_s1, b_k0, b_k_s1;
+  long long o_s0, o_s1;               // output element offsets per (outer, inner)
+  float alpha;                        // accumulator scale (0 = 1)
 };
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -253,12 +260,19 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mA0h, const __grid_constant__
     {
       uint32_t ia = 0, ib = 0;   // running stage counters (whole warp runs the loop; one elected lane issues)
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        const int m0 = (tile % p.m_tiles) * TC_BM, n0 = (tile / p.m_tiles) * NCH * TC_NC;
+        int lt = tile, a_r = 0, a_k = 0, b_r = 0, b_k = 0;
+        if (p.bat_inner) {
+          const int bat = tile / p.bat_tiles, bo = bat / p.bat_inner, bi = bat - bo * p.bat_inner;
+          lt = tile - bat * p.bat_tiles;
+          a_r = bo * p.a_row_s0 + bi * p.a_row_s1; a_k = bi * p.a_k_s1;
+          b_r = bo * p.b_row_s0 + bi * p.b_row_s1; b_k = p.b_k0 + bi * p.b_k_s1;
+        }
+        const int m0 = (lt % p.m_tiles) * TC_BM + a_r, n0 = (lt / p.m_tiles) * NCH * TC_NC + b_r;
         for (int kb = 0; kb < KB; ++kb) {
           const uint32_t sa = ia % TC_SA, pa = (ia / TC_SA) & 1u;
           mbar_wait(a_empty(sa), pa ^ 1u);
           const bool first = kb < p.KB0;
-          const int ka = (first ? kb : kb - p.KB0) * TC_BK;
+          const int ka = (first ? kb : kb - p.KB0) * TC_BK + a_k;
           const uint32_t dstA = a_ring + sa * 2 * TC_PLANE_BYTES;
           if (elect_one()) {
             mbar_expect_tx(a_full(sa), stage_bytes);
@@ -273,8 +287,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mA0h, const __grid_constant__
             const uint32_t dstB = b_ring + sb * 2 * TC_PLANE_BYTES;
             if (elect_one()) {
               mbar_expect_tx(b_full(sb), stage_bytes);
-              tma_load_2d(dstB, &mBh, b_full(sb), kb * TC_BK, n0 + c * TC_NC);
-              if (p.planes == 2) tma_load_2d(dstB + TC_PLANE_BYTES, &mBl, b_full(sb), kb * TC_BK, n0 + c * TC_NC);
+              tma_load_2d(dstB, &mBh, b_full(sb), kb * TC_BK + b_k, n0 + c * TC_NC);
+              if (p.planes == 2) tma_load_2d(dstB + TC_PLANE_BYTES, &mBl, b_full(sb), kb * TC_BK + b_k, n0 + c * TC_NC);
             }
             __syncwarp();
             ++ib;
@@ -327,8 +341,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mA0h, const __grid_constant__
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
       mbar_wait(tmem_full, it & 1u);
       tc_fence_after();
-      const long long m = (long long)(tile % p.m_tiles) * TC_BM + row_in_tile;
-      const int n0 = (tile / p.m_tiles) * NCH * TC_NC;
+      int lt = tile; long long o_off = 0;
+      if (p.bat_inner) {
+        const int bat = tile / p.bat_tiles, bo = bat / p.bat_inner, bi = bat - bo * p.bat_inner;
+        lt = tile - bat * p.bat_tiles;
+        o_off = bo * p.o_s0 + bi * p.o_s1;
+      }
+      const long long m = (long long)(lt % p.m_tiles) * TC_BM + row_in_tile;
+      const int n0 = (lt / p.m_tiles) * NCH * TC_NC;
       const bool valid = m < p.M;
       const float* add_i = nullptr; const float* add_j = nullptr;
       float emask = 1.f;
@@ -352,12 +372,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mA0h, const __grid_constant__
           tmem_ld32(trow + (uint32_t)c0, r);
           const int n = n0 + c0;
           if (valid && n < p.n_valid) {
-            float* orow = p.out_f32 + m * p.ldo + n;
+            float* orow = p.out_f32 + o_off + m * p.ldo + n;
             const float* rrow = p.residual ? p.residual + m * p.ldr + n : nullptr;
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
               if (n + q * 4 < p.n_valid) {     // n_valid is a multiple of 4 for every node linear routed here
                 float4 v = make_float4(__uint_as_float(r[q * 4 + 0]), __uint_as_float(r[q * 4 + 1]), __uint_as_float(r[q * 4 + 2]), __uint_as_float(r[q * 4 + 3]));
+                if (p.alpha != 0.f) { v.x *= p.alpha; v.y *= p.alpha; v.z *= p.alpha; v.w *= p.alpha; }
                 if (p.bias) { const float4 b4 = *reinterpret_cast<const float4*>(p.bias + n + q * 4); v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w; }
                 if (p.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
                 v.x *= rm; v.y *= rm; v.z *= rm; v.w *= rm;
@@ -1082,18 +1103,10 @@ tc_embed_fused_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_cons
     const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16);
     const int cb = half * 64;
     const uint32_t stage = stats + 2048u + (uint32_t)(warp - 2) * 4096u;     // this warp's store-staging buffer
-    for (uint32_t it = 0; it < n_my; ++it) {
+    // Software pipeline: the activation of tile it+1 is converted before the LayerNorm of tile it, so the second GEMM of tile it+1
+    // runs on the tensor pipe while these warps normalise and store tile it.
+    auto convert = [&](uint32_t it) {
       const uint32_t x = it & 1u, ph = (it >> 1) & 1u;
-      const long long m = (long long)((int)blockIdx.x + (int)it * (int)gridDim.x) * TC_BM + row;
-      const bool valid = m < p.E;
-      float emask = 0.f;
-      if (valid) {
-        const long long nn = (long long)p.nres * p.nres;
-        const long long b = m / nn;
-        const int rem = (int)(m - b * nn);
-        const int ri = rem / p.nres, rj = rem - ri * p.nres;
-        emask = p.res_mask[b * p.nres + ri] * p.res_mask[b * p.nres + rj];
-      }
       // ---- relu(H1 + b2) -> bf16 hi/lo A image over this warp's own 64 columns (hi words [0,32), lo words [32,64)) ----
       mbar_wait(h1_full(x), ph);
       tc_fence_after();
@@ -1125,6 +1138,19 @@ tc_embed_fused_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_cons
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(c_full(x));
+    };
+    auto layernorm = [&](uint32_t it) {
+      const uint32_t x = it & 1u, ph = (it >> 1) & 1u;
+      const long long m = (long long)((int)blockIdx.x + (int)it * (int)gridDim.x) * TC_BM + row;
+      const bool valid = m < p.E;
+      float emask = 0.f;
+      if (valid) {
+        const long long nn = (long long)p.nres * p.nres;
+        const long long b = m / nn;
+        const int rem = (int)(m - b * nn);
+        const int ri = rem / p.nres, rj = rem - ri * p.nres;
+        emask = p.res_mask[b * p.nres + ri] * p.res_mask[b * p.nres + rj];
+      }
       // ---- LayerNorm(Y + b4) * mask -> z planes.  Two warps per quadrant split the 128 columns; partial statistics meet in smem ----
       float v[64];
       mbar_wait(y_full(x), ph);
@@ -1185,6 +1211,11 @@ tc_embed_fused_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_cons
         warp_store_rows64(stage, hw, p.out_hi, m_warp, cb, p.E, lane);
         if (p.planes == 2) warp_store_rows64(stage, lw, p.out_lo, m_warp, cb, p.E, lane);
       }
+    };
+    if (n_my > 0) convert(0);
+    for (uint32_t it = 0; it < n_my; ++it) {
+      if (it + 1 < n_my) convert(it + 1);
+      layernorm(it);
       // the stats slots are rewritten by this pair only after its next bar.sync pair, i.e. after both have read them
     }
   }
@@ -1212,6 +1243,45 @@ __global__ void split_planes_kernel(const float* __restrict__ x, int ld, long lo
   split2_bf16(v.z, v.w, h1, l1);
   *reinterpret_cast<uint2*>(hi + m * K + k) = make_uint2(h0, h1);
   if (lo) *reinterpret_cast<uint2*>(lo + m * K + k) = make_uint2(l0, l1);
+}
+
+// fp32 [M, ld] (first Kv columns valid) -> bf16 hi/lo planes [M, Kp], zero beyond Kv  (attention probabilities: A operand of a·v)
+__global__ void split_pad_planes_kernel(const float* __restrict__ x, int ld, long long M, int Kv, int Kp, __nv_bfloat16* __restrict__ hi,
+                                        __nv_bfloat16* __restrict__ lo) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // four columns
+  const int k4 = Kp / 4;
+  if (i >= M * k4) return;
+  const long long m = i / k4;
+  const int k = (int)(i - m * k4) * 4;
+  float v[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) v[e] = (k + e < Kv) ? x[m * ld + k + e] : 0.f;
+  uint32_t h0, l0, h1, l1;
+  split2_bf16(v[0], v[1], h0, l0);
+  split2_bf16(v[2], v[3], h1, l1);
+  *reinterpret_cast<uint2*>(hi + m * Kp + k) = make_uint2(h0, h1);
+  *reinterpret_cast<uint2*>(lo + m * Kp + k) = make_uint2(l0, l1);
+}
+
+// IPA values, transposed per (sample, head) into K-major planes for a·v:  vt[((b*H + h)*256 + c), j] = v[b, j, h, c], zero for j >= N.
+// proj is the fused projection output [B*N, PROJ_ALL]; v of head h sits at column PROJ_Q + h*512 + 256.
+__global__ void vt_planes_kernel(const float* __restrict__ proj, int N, int Kp, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+  __shared__ float tile[32][33];
+  const int bh = blockIdx.z, b = bh / H, hh = bh - b * H;
+  const int j0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;   // 32 x 8
+  for (int r = ty; r < 32; r += 8) {
+    const int j = j0 + r;
+    tile[r][tx] = j < N ? proj[((long long)b * N + j) * PROJ_ALL + PROJ_Q + hh * 2 * C_HID + C_HID + c0 + tx] : 0.f;
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const float v = tile[tx][r];                  // (j = j0 + tx, c = c0 + r)
+    __nv_bfloat16 h, l;
+    split_bf16(v, h, l);
+    const long long o = ((long long)bh * C_HID + c0 + r) * Kp + j0 + tx;
+    hi[o] = h; lo[o] = l;
+  }
 }
 
 // planes -> fp32 (debug taps / export)
@@ -1275,6 +1345,8 @@ struct TcWeights {
   TcMat wb[4];                    // IPA linear_b padded to [128][128] (rows 0..7 real): pair bias z·Wb^T on the tensor cores (UMMA N = 16)
 };
 
+constexpr int TC_QKV = PROJ_Q + PROJ_KV;   // q | k,v columns of the fused IPA projection (2048 + 4096)
+
 struct TcWorkspace {
   char* base = nullptr;
   long long E = 0;
@@ -1285,6 +1357,10 @@ struct TcWorkspace {
   __nv_bfloat16 *z_hi, *z_lo, *h1_hi, *h1_lo, *h2_hi, *h2_lo;
   CUtensorMap m_z_h, m_z_l, m_h1_h, m_h1_l, m_h2_h, m_h2_l;      // K = 128 / 384 / 384
   CUtensorMap m_e0_h, m_e0_l, m_e1_h, m_e1_l;                     // embedder staging viewed as [E,128] inside h1 / h2
+  // attention GEMMs (always split precision): q|k|v projection planes [R, 6144], probabilities [B*H*N, Kp], values^T [B*H*256, Kp]
+  int Kp = 0;
+  __nv_bfloat16 *pj_hi = nullptr, *pj_lo = nullptr, *at_hi = nullptr, *at_lo = nullptr, *vt_hi = nullptr, *vt_lo = nullptr;
+  CUtensorMap m_pj_h, m_pj_l, m_at_h, m_at_l, m_vt_h, m_vt_l;
 };
 
 inline void tc_free_weights(TcWeights& w) {
@@ -1366,7 +1442,9 @@ inline size_t tc_hidden_width() { return getenv("FD_TC_UNFUSED") ? (size_t)ET_HI
 inline size_t tc_workspace_bytes(int B, int N) {
   const size_t E = (size_t)B * N * N, R = (size_t)B * N;
   auto al = [](size_t x) { return (x + 1023) & ~(size_t)1023; };
-  return 2 * al(E * C_Z * 2) + 4 * al(E * tc_hidden_width() * 2) + 2 * al(R * TC_AMAX_K * 2) + al(E * H * 4) + 1024;
+  const size_t Kp = ((size_t)N + 63) / 64 * 64;
+  return 2 * al(E * C_Z * 2) + 4 * al(E * tc_hidden_width() * 2) + 2 * al(R * TC_AMAX_K * 2) + al(E * H * 4) + 1024 +
+         2 * al(R * TC_QKV * 2) + 2 * al(R * H * Kp * 2) + 2 * al((size_t)B * H * C_HID * Kp * 2);
 }
 inline int tc_bind_workspace(TcWorkspace& w, char* p, int B, int N) {
   const size_t E = (size_t)B * N * N;
@@ -1384,8 +1462,19 @@ inline int tc_bind_workspace(TcWorkspace& w, char* p, int B, int N) {
   w.a_hi = (__nv_bfloat16*)p; p += al((size_t)w.R * TC_AMAX_K * 2);
   w.a_lo = (__nv_bfloat16*)p; p += al((size_t)w.R * TC_AMAX_K * 2);
   w.pbias = (float*)p; p += al(E * H * 4);
+  w.Kp = (N + 63) / 64 * 64;
+  const size_t R = (size_t)w.R, Kp = (size_t)w.Kp;
+  w.pj_hi = (__nv_bfloat16*)p; p += al(R * TC_QKV * 2);
+  w.pj_lo = (__nv_bfloat16*)p; p += al(R * TC_QKV * 2);
+  w.at_hi = (__nv_bfloat16*)p; p += al(R * H * Kp * 2);
+  w.at_lo = (__nv_bfloat16*)p; p += al(R * H * Kp * 2);
+  w.vt_hi = (__nv_bfloat16*)p; p += al((size_t)B * H * C_HID * Kp * 2);
+  w.vt_lo = (__nv_bfloat16*)p; p += al((size_t)B * H * C_HID * Kp * 2);
   w.a_maps.clear();
   int rc = 0;
+  rc |= tc_make_map(&w.m_pj_h, w.pj_hi, R, TC_QKV); rc |= tc_make_map(&w.m_pj_l, w.pj_lo, R, TC_QKV);
+  rc |= tc_make_map(&w.m_at_h, w.at_hi, R * H, Kp); rc |= tc_make_map(&w.m_at_l, w.at_lo, R * H, Kp);
+  rc |= tc_make_map(&w.m_vt_h, w.vt_hi, (uint64_t)B * H * C_HID, Kp); rc |= tc_make_map(&w.m_vt_l, w.vt_lo, (uint64_t)B * H * C_HID, Kp);
   for (int K : {128, 256, 320, 384, IPA_FEAT}) {
     std::pair<CUtensorMap, CUtensorMap> mp;
     rc |= tc_make_map(&mp.first, w.a_hi, (uint64_t)w.R, (uint64_t)K);
@@ -1402,16 +1491,20 @@ inline int tc_bind_workspace(TcWorkspace& w, char* p, int B, int N) {
   return rc;
 }
 
-inline int tc_launch(const CUtensorMap& a0h, const CUtensorMap& a0l, const CUtensorMap& a1h, const CUtensorMap& a1l, const TcMat& Wt,
-                     TcGemmParams p, cudaStream_t st, long long* launches) {
+inline int tc_launch_maps(const CUtensorMap& a0h, const CUtensorMap& a0l, const CUtensorMap& a1h, const CUtensorMap& a1l, const CUtensorMap& bh,
+                          const CUtensorMap& bl, TcGemmParams p, cudaStream_t st, long long* launches) {
   if (p.epi != TC_EPI_F32) {
     p.m_tiles = (p.M + TC_BM - 1) / TC_BM; p.nch = p.N / TC_NC; p.num_tiles = p.m_tiles; p.n_valid = p.N;
   }
   if (p.mma_n == 0) p.mma_n = TC_NC;
   const int grid = p.num_tiles < g_tc_sms ? p.num_tiles : g_tc_sms;
-  tc_gemm_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(a0h, a0l, a1h, a1l, Wt.mh, Wt.ml, p);
+  tc_gemm_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(a0h, a0l, a1h, a1l, bh, bl, p);
   if (launches) ++*launches;
   return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+inline int tc_launch(const CUtensorMap& a0h, const CUtensorMap& a0l, const CUtensorMap& a1h, const CUtensorMap& a1l, const TcMat& Wt,
+                     TcGemmParams p, cudaStream_t st, long long* launches) {
+  return tc_launch_maps(a0h, a0l, a1h, a1l, Wt.mh, Wt.ml, p, st, launches);
 }
 
 // Edge embedder (model/score_network.py:79-86): layer 0 = table lookup kernel -> bf16 planes; layers 2, 4 on tensor cores.
@@ -1530,6 +1623,41 @@ inline int tc_ipa_edge(const TcWeights& tw, TcWorkspace& w, int blk, float* L, c
   else ipa_edge2_kernel<1><<<dim3(N, B), 256, smem, st>>>(z, L, w.pbias, qp, kp, res_mask, gamma, WdT, bd, feats, N, Np);
   if (launches) ++*launches;
   return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+
+// IPA scalar attention logits on the tensor cores (model/ipa_pytorch.py:376-383): per (sample, head) a [N,N] = q·k^T GEMM with K = 256,
+// both operands from the split projection planes, scaled by sqrt(1/(3*c_hidden)), fp32 out into L [B,H,N,Np].
+inline int tc_ipa_logits(TcWorkspace& w, const float* proj, float* L, int B, int N, int Np, float alpha, cudaStream_t st, long long* launches) {
+  const long long n4 = (long long)w.R * (TC_QKV / 4);
+  split_planes_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(proj, PROJ_ALL, w.R, TC_QKV, w.pj_hi, w.pj_lo);
+  if (launches) ++*launches;
+  TcGemmParams p{};
+  p.M = N; p.N = 128; p.KB0 = C_HID / TC_BK; p.KB1 = 0; p.planes = 2; p.epi = TC_EPI_F32;
+  p.m_tiles = (N + TC_BM - 1) / TC_BM; p.nch = 1;
+  const int n_groups = (N + TC_NC - 1) / TC_NC;
+  p.bat_inner = H; p.bat_tiles = p.m_tiles * n_groups; p.num_tiles = B * H * p.bat_tiles;
+  p.a_row_s0 = N; p.a_row_s1 = 0; p.a_k_s1 = C_HID;
+  p.b_row_s0 = N; p.b_row_s1 = 0; p.b_k0 = PROJ_Q; p.b_k_s1 = 2 * C_HID;
+  p.n_valid = N; p.out_f32 = L; p.ldo = Np; p.o_s0 = (long long)H * N * Np; p.o_s1 = (long long)N * Np; p.alpha = alpha;
+  return tc_launch_maps(w.m_pj_h, w.m_pj_l, w.m_pj_h, w.m_pj_l, w.m_pj_h, w.m_pj_l, p, st, launches);
+}
+
+// IPA o = a·v on the tensor cores (model/ipa_pytorch.py:433-436): per (sample, head) [N, 256] = a [N, N] · v [N, 256], K = N padded to a
+// multiple of 64 with zeros in both operands.  Output lands in feats[:, h*256 : (h+1)*256].
+inline int tc_ipa_av(TcWorkspace& w, const float* proj, const float* L, float* feats, int B, int N, int Np, cudaStream_t st, long long* launches) {
+  const long long M = (long long)w.R * H;
+  const long long n4 = M * (w.Kp / 4);
+  split_pad_planes_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(L, Np, M, N, w.Kp, w.at_hi, w.at_lo);
+  vt_planes_kernel<<<dim3(w.Kp / 32, C_HID / 32, B * H), dim3(32, 8), 0, st>>>(proj, N, w.Kp, w.vt_hi, w.vt_lo);
+  if (launches) *launches += 2;
+  TcGemmParams p{};
+  p.M = N; p.N = C_HID; p.KB0 = w.Kp / TC_BK; p.KB1 = 0; p.planes = 2; p.epi = TC_EPI_F32;
+  p.m_tiles = (N + TC_BM - 1) / TC_BM; p.nch = 2;
+  p.bat_inner = H; p.bat_tiles = p.m_tiles; p.num_tiles = B * H * p.bat_tiles;
+  p.a_row_s0 = H * N; p.a_row_s1 = N; p.a_k_s1 = 0;
+  p.b_row_s0 = H * C_HID; p.b_row_s1 = C_HID; p.b_k0 = 0; p.b_k_s1 = 0;
+  p.n_valid = C_HID; p.out_f32 = feats; p.ldo = IPA_FEAT; p.o_s0 = (long long)N * IPA_FEAT; p.o_s1 = C_HID;
+  return tc_launch_maps(w.m_at_h, w.m_at_l, w.m_at_h, w.m_at_l, w.m_vt_h, w.m_vt_l, p, st, launches);
 }
 
 }  // namespace fd
