@@ -639,16 +639,16 @@ static int forward_impl(fd_context* h, int B, int N, const float* rigids_t, cons
       g.B = w.proj + PROJ_Q + C_HID; g.ldb = PROJ_ALL; g.sB0 = (long long)N * PROJ_ALL; g.sB1 = 2 * C_HID;
       g.C = w.feats; g.ldc = IPA_FEAT; g.sC0 = (long long)N * IPA_FEAT; g.sC1 = C_HID;
       g.M = N; g.N = C_HID; g.K = N; g.nb0 = B; g.nb1 = H;
-      if (tc) {
-        if (!f.err && tc_ipa_av(w.tc, w.proj, w.L, w.feats, B, N, Np, st, &h->launches))
-          f.err = fail(FD_ECUDA, "ipa a.v (tensor-core) launch failed: %s", cudaGetErrorString(cudaGetLastError()));
-      } else {
-        f.gemm(g, false);
-      }
       GemmArgs p = g;   // o_pt (global) = a · v_pts
       p.B = w.vp; p.ldb = H * PV * 3; p.sB0 = (long long)N * H * PV * 3; p.sB1 = PV * 3;
       p.C = w.optg; p.ldc = H * PV * 3; p.sC0 = (long long)N * H * PV * 3; p.sC1 = PV * 3; p.N = PV * 3;
-      f.gemm(p, false);
+      if (tc) {
+        if (!f.err && tc_ipa_av(w.tc, w.proj, w.vp, w.L, w.feats, w.optg, B, N, Np, st, &h->launches))
+          f.err = fail(FD_ECUDA, "ipa a.v (tensor-core) launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+      } else {
+        f.gemm(g, false);
+        f.gemm(p, false);
+      }
       ipa_finish_kernel<<<(unsigned)R, 96, 0, st>>>(w.optg, w.quat, w.trans, w.feats, R);
       f.check("ipa_finish");
     }
@@ -672,7 +672,12 @@ static int forward_impl(fd_context* h, int B, int N, const float* rigids_t, cons
         g.B = w.qkv + TF_D; g.ldb = 3 * TF_D; g.sB0 = (long long)N * 3 * TF_D; g.sB1 = TF_DH;
         g.C = w.S; g.ldc = Np; g.sC0 = (long long)TF_H * N * Np; g.sC1 = (long long)N * Np;
         g.M = N; g.N = N; g.K = TF_DH; g.nb0 = B; g.nb1 = TF_H; g.alpha = (float)(1.0 / sqrt((double)TF_DH));
-        f.gemm(g);
+        if (tc) {
+          if (!f.err && tc_tf_logits(w.tc, w.qkv, w.S, B, N, Np, st, &h->launches))
+            f.err = fail(FD_ECUDA, "transformer logits (tensor-core) launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+        } else {
+          f.gemm(g);
+        }
         const long long rows = (long long)B * TF_H * N;
         softmax_rows_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(w.S, Np, N, rows, (long long)TF_H * N, res_mask);
         f.check("softmax_rows");
@@ -681,7 +686,12 @@ static int forward_impl(fd_context* h, int B, int N, const float* rigids_t, cons
         v.B = w.qkv + 2 * TF_D; v.ldb = 3 * TF_D; v.sB0 = (long long)N * 3 * TF_D; v.sB1 = TF_DH;
         v.C = w.y320; v.ldc = TF_D; v.sC0 = (long long)N * TF_D; v.sC1 = TF_DH;
         v.M = N; v.N = TF_DH; v.K = N; v.nb0 = B; v.nb1 = TF_H;
-        f.gemm(v, false);
+        if (tc) {
+          if (!f.err && tc_tf_values(w.tc, w.qkv, w.S, w.y320, B, N, Np, st, &h->launches))
+            f.err = fail(FD_ECUDA, "transformer values (tensor-core) launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+        } else {
+          f.gemm(v, false);
+        }
       }
       f.linear(w.y320, TF_D, T.out_proj, TF_D, TF_D, w.ff, TF_D, R, false, x, TF_D);       // x + attn
       f.ln(320, w.ff, TF_D, xo, TF_D, T.norm1, R);

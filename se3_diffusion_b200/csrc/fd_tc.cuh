@@ -223,9 +223,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mA0h, const __grid_constant__
   auto a_empty = [&](int s) { return bar0 + 8u * (TC_SA + s); };
   auto b_full = [&](int s) { return bar0 + 8u * (2 * TC_SA + s); };
   auto b_empty = [&](int s) { return bar0 + 8u * (2 * TC_SA + TC_SB + s); };
-  const uint32_t tmem_full = bar0 + 8u * (2 * TC_SA + 2 * TC_SB);
-  const uint32_t tmem_empty = tmem_full + 8u;
-  const uint32_t tmem_ptr_addr = tmem_empty + 8u;
+  // accumulators are double-buffered in tensor memory (two 256-column halves) whenever a work item needs <= 256 columns
+  auto tmem_full = [&](uint32_t x) { return bar0 + 8u * (2 * TC_SA + 2 * TC_SB + x); };
+  auto tmem_empty = [&](uint32_t x) { return bar0 + 8u * (2 * TC_SA + 2 * TC_SB + 2 + x); };
+  const uint32_t tmem_ptr_addr = bar0 + 8u * (2 * TC_SA + 2 * TC_SB + 4);
   const uint32_t wb_smem = bar0 + 256u;           // optional linear_b image [8][128] fp32 (LN epilogue's pair bias)
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
@@ -233,13 +234,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mA0h, const __grid_constant__
   if (p.pbias)
     for (int i = threadIdx.x; i < H * C_Z; i += TC_THREADS) asm volatile("st.shared.f32 [%0], %1;" ::"r"(wb_smem + 4u * i), "f"(p.wb[i]) : "memory");
   const int NCH = p.nch;
+  const bool dbuf = NCH * TC_NC <= 256;
   const uint32_t stage_bytes = (uint32_t)p.planes * TC_PLANE_BYTES;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < TC_SA; ++s) { mbar_init(a_full(s), 1); mbar_init(a_empty(s), 1); }
     for (int s = 0; s < TC_SB; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
-    mbar_init(tmem_full, 1);
-    mbar_init(tmem_empty, 4);     // one arrive per epilogue warp
+    for (uint32_t x = 0; x < 2; ++x) { mbar_init(tmem_full(x), 1); mbar_init(tmem_empty(x), 4); }   // empty: one arrive per epilogue warp
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     tma_prefetch_desc(&mA0h); tma_prefetch_desc(&mBh);
     if (p.planes == 2) { tma_prefetch_desc(&mA0l); tma_prefetch_desc(&mBl); }
@@ -302,7 +303,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mA0h, const __grid_constant__
       const uint32_t idesc = make_idesc_bf16(TC_BM, p.mma_n);
       uint32_t ia = 0, ib = 0, it = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
-        mbar_wait(tmem_empty, (it & 1u) ^ 1u);      // epilogue has drained the previous tile's accumulators
+        const uint32_t buf = dbuf ? (it & 1u) : 0u, use = dbuf ? (it >> 1) : it;
+        mbar_wait(tmem_empty(buf), (use & 1u) ^ 1u);      // epilogue has drained this half's previous accumulators
         tc_fence_after();
         for (int kb = 0; kb < KB; ++kb) {
           const uint32_t sa = ia % TC_SA, pa = (ia / TC_SA) & 1u;
@@ -314,7 +316,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mA0h, const __grid_constant__
             mbar_wait(b_full(sb), pb);
             tc_fence_after();
             const uint32_t bH = b_ring + sb * 2 * TC_PLANE_BYTES, bL = bH + TC_PLANE_BYTES;
-            const uint32_t d = tmem_base + (uint32_t)(c * TC_NC);
+            const uint32_t d = tmem_base + 256u * buf + (uint32_t)(c * TC_NC);
             const uint64_t dAH = make_sw128_desc(aH), dAL = make_sw128_desc(aL), dBH = make_sw128_desc(bH), dBL = make_sw128_desc(bL);
             if (elect_one()) {
 #pragma unroll
@@ -330,7 +332,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mA0h, const __grid_constant__
           tc_commit_elect(a_empty(sa));
           ++ia;
         }
-        tc_commit_elect(tmem_full);           // accumulators complete -> epilogue
+        tc_commit_elect(tmem_full(buf));      // accumulators complete -> epilogue
       }
     }
   } else {
@@ -339,7 +341,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mA0h, const __grid_constant__
     const int row_in_tile = quad * 32 + lane;
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
-      mbar_wait(tmem_full, it & 1u);
+      const uint32_t buf = dbuf ? (it & 1u) : 0u, use = dbuf ? (it >> 1) : it;
+      mbar_wait(tmem_full(buf), use & 1u);
       tc_fence_after();
       int lt = tile; long long o_off = 0;
       if (p.bat_inner) {
@@ -363,26 +366,36 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mA0h, const __grid_constant__
         }
         if (p.res_mask) emask = p.res_mask[b * p.nres + ri] * p.res_mask[b * p.nres + rj];
       }
-      const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16);
+      const uint32_t trow = tmem_base + 256u * buf + ((uint32_t)(quad * 32) << 16);
       if (p.epi == TC_EPI_F32) {
         const float rm = (valid && p.rowmask) ? p.rowmask[m] : 1.f;
         const int ncols = min(NCH * TC_NC, ((p.n_valid - n0 + 31) / 32) * 32);     // skip accumulator columns beyond the valid width
         for (int c0 = 0; c0 < ncols; c0 += 32) {
+          const int n = n0 + c0;
+          const bool act = valid && n < p.n_valid;
+          // bias / residual of this 32-column group are requested before the accumulator read: their latencies overlap instead of
+          // serialising behind the stores (the compiler cannot hoist them itself: out_f32 may alias)
+          float4 bv[8], rv[8];
+          const float* rrow = (act && p.residual) ? p.residual + m * p.ldr + n : nullptr;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const bool in = act && n + q * 4 < p.n_valid;     // n_valid is a multiple of 4 for every linear routed here
+            bv[q] = (in && p.bias) ? __ldg(reinterpret_cast<const float4*>(p.bias + n + q * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            rv[q] = (in && rrow) ? *reinterpret_cast<const float4*>(rrow + q * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
           uint32_t r[32];
           tmem_ld32(trow + (uint32_t)c0, r);
-          const int n = n0 + c0;
-          if (valid && n < p.n_valid) {
+          if (act) {
             float* orow = p.out_f32 + o_off + m * p.ldo + n;
-            const float* rrow = p.residual ? p.residual + m * p.ldr + n : nullptr;
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
-              if (n + q * 4 < p.n_valid) {     // n_valid is a multiple of 4 for every node linear routed here
+              if (n + q * 4 < p.n_valid) {
                 float4 v = make_float4(__uint_as_float(r[q * 4 + 0]), __uint_as_float(r[q * 4 + 1]), __uint_as_float(r[q * 4 + 2]), __uint_as_float(r[q * 4 + 3]));
                 if (p.alpha != 0.f) { v.x *= p.alpha; v.y *= p.alpha; v.z *= p.alpha; v.w *= p.alpha; }
-                if (p.bias) { const float4 b4 = *reinterpret_cast<const float4*>(p.bias + n + q * 4); v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w; }
+                v.x += bv[q].x; v.y += bv[q].y; v.z += bv[q].z; v.w += bv[q].w;
                 if (p.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
                 v.x *= rm; v.y *= rm; v.z *= rm; v.w *= rm;
-                if (rrow) { const float4 r4 = *reinterpret_cast<const float4*>(rrow + q * 4); v.x += r4.x; v.y += r4.y; v.z += r4.z; v.w += r4.w; }
+                v.x += rv[q].x; v.y += rv[q].y; v.z += rv[q].z; v.w += rv[q].w;
                 *reinterpret_cast<float4*>(orow + q * 4) = v;
               }
             }
@@ -480,7 +493,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mA0h, const __grid_constant__
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tmem_empty);
+      if (lane == 0) mbar_arrive(tmem_empty(buf));
     }
   }
   tc_fence_before();
@@ -1263,25 +1276,44 @@ __global__ void split_pad_planes_kernel(const float* __restrict__ x, int ld, lon
   *reinterpret_cast<uint2*>(lo + m * Kp + k) = make_uint2(l0, l1);
 }
 
-// IPA values, transposed per (sample, head) into K-major planes for a·v:  vt[((b*H + h)*256 + c), j] = v[b, j, h, c], zero for j >= N.
-// proj is the fused projection output [B*N, PROJ_ALL]; v of head h sits at column PROJ_Q + h*512 + 256.
-__global__ void vt_planes_kernel(const float* __restrict__ proj, int N, int Kp, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+// Values transposed per (sample, head) into K-major planes for the probability·value GEMMs:
+//   vt[(bh*dhp + c), j] = x[(b*N + j)*ld + col0 + h*hstride + c]  for c < dh, j < N; zero elsewhere (c < dhp, j < Kp).
+__global__ void vt_planes_kernel(const float* __restrict__ x, int ld, int col0, int hstride, int nheads, int dh, int dhp, int N, int Kp,
+                                 __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
   __shared__ float tile[32][33];
-  const int bh = blockIdx.z, b = bh / H, hh = bh - b * H;
+  const int bh = blockIdx.z, b = bh / nheads, hh = bh - b * nheads;
   const int j0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
   const int tx = threadIdx.x, ty = threadIdx.y;   // 32 x 8
   for (int r = ty; r < 32; r += 8) {
     const int j = j0 + r;
-    tile[r][tx] = j < N ? proj[((long long)b * N + j) * PROJ_ALL + PROJ_Q + hh * 2 * C_HID + C_HID + c0 + tx] : 0.f;
+    tile[r][tx] = (j < N && c0 + tx < dh) ? x[((long long)b * N + j) * ld + col0 + hh * hstride + c0 + tx] : 0.f;
   }
   __syncthreads();
   for (int r = ty; r < 32; r += 8) {
     const float v = tile[tx][r];                  // (j = j0 + tx, c = c0 + r)
     __nv_bfloat16 h, l;
     split_bf16(v, h, l);
-    const long long o = ((long long)bh * C_HID + c0 + r) * Kp + j0 + tx;
+    const long long o = ((long long)bh * dhp + c0 + r) * Kp + j0 + tx;
     hi[o] = h; lo[o] = l;
   }
+}
+
+// Per-head zero-padded split of the sequence transformer's q and k:  out[m, g*dhp + c] = x[m*ld + g*dh + c] (c < dh), 0 otherwise,
+// for the ngroups = 2*heads consecutive dh-wide groups (q heads then k heads).  K-blocks of 64 then never straddle two heads.
+__global__ void split_heads_pad_kernel(const float* __restrict__ x, int ld, long long M, int ngroups, int dh, int dhp,
+                                       __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // four columns
+  const int W = ngroups * dhp, k4 = W / 4;
+  if (i >= M * k4) return;
+  const long long m = i / k4;
+  const int k = (int)(i - m * k4) * 4, g = k / dhp, c = k - g * dhp;      // dh and dhp are multiples of 4
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (c < dh) v = *reinterpret_cast<const float4*>(x + m * ld + g * dh + c);
+  uint32_t h0, l0, h1, l1;
+  split2_bf16(v.x, v.y, h0, l0);
+  split2_bf16(v.z, v.w, h1, l1);
+  *reinterpret_cast<uint2*>(hi + m * W + k) = make_uint2(h0, h1);
+  *reinterpret_cast<uint2*>(lo + m * W + k) = make_uint2(l0, l1);
 }
 
 // planes -> fp32 (debug taps / export)
@@ -1361,6 +1393,9 @@ struct TcWorkspace {
   int Kp = 0;
   __nv_bfloat16 *pj_hi = nullptr, *pj_lo = nullptr, *at_hi = nullptr, *at_lo = nullptr, *vt_hi = nullptr, *vt_lo = nullptr;
   CUtensorMap m_pj_h, m_pj_l, m_at_h, m_at_l, m_vt_h, m_vt_l;
+  __nv_bfloat16 *vp_hi = nullptr, *vp_lo = nullptr;                 // IPA value points^T [B*H*64, Kp] (36 real rows per head)
+  CUtensorMap m_vp_h, m_vp_l;
+  CUtensorMap m_tq_h, m_tq_l;                                       // sequence-transformer q|k head-padded planes [R, 1024] (inside pj)
 };
 
 inline void tc_free_weights(TcWeights& w) {
@@ -1444,7 +1479,7 @@ inline size_t tc_workspace_bytes(int B, int N) {
   auto al = [](size_t x) { return (x + 1023) & ~(size_t)1023; };
   const size_t Kp = ((size_t)N + 63) / 64 * 64;
   return 2 * al(E * C_Z * 2) + 4 * al(E * tc_hidden_width() * 2) + 2 * al(R * TC_AMAX_K * 2) + al(E * H * 4) + 1024 +
-         2 * al(R * TC_QKV * 2) + 2 * al(R * H * Kp * 2) + 2 * al((size_t)B * H * C_HID * Kp * 2);
+         2 * al(R * TC_QKV * 2) + 2 * al(R * H * Kp * 2) + 2 * al((size_t)B * H * C_HID * Kp * 2) + 2 * al((size_t)B * H * 64 * Kp * 2);
 }
 inline int tc_bind_workspace(TcWorkspace& w, char* p, int B, int N) {
   const size_t E = (size_t)B * N * N;
@@ -1470,8 +1505,12 @@ inline int tc_bind_workspace(TcWorkspace& w, char* p, int B, int N) {
   w.at_lo = (__nv_bfloat16*)p; p += al(R * H * Kp * 2);
   w.vt_hi = (__nv_bfloat16*)p; p += al((size_t)B * H * C_HID * Kp * 2);
   w.vt_lo = (__nv_bfloat16*)p; p += al((size_t)B * H * C_HID * Kp * 2);
+  w.vp_hi = (__nv_bfloat16*)p; p += al((size_t)B * H * 64 * Kp * 2);
+  w.vp_lo = (__nv_bfloat16*)p; p += al((size_t)B * H * 64 * Kp * 2);
   w.a_maps.clear();
   int rc = 0;
+  rc |= tc_make_map(&w.m_vp_h, w.vp_hi, (uint64_t)B * H * 64, Kp); rc |= tc_make_map(&w.m_vp_l, w.vp_lo, (uint64_t)B * H * 64, Kp);
+  rc |= tc_make_map(&w.m_tq_h, w.pj_hi, R, 2 * TF_H * 128); rc |= tc_make_map(&w.m_tq_l, w.pj_lo, R, 2 * TF_H * 128);
   rc |= tc_make_map(&w.m_pj_h, w.pj_hi, R, TC_QKV); rc |= tc_make_map(&w.m_pj_l, w.pj_lo, R, TC_QKV);
   rc |= tc_make_map(&w.m_at_h, w.at_hi, R * H, Kp); rc |= tc_make_map(&w.m_at_l, w.at_lo, R * H, Kp);
   rc |= tc_make_map(&w.m_vt_h, w.vt_hi, (uint64_t)B * H * C_HID, Kp); rc |= tc_make_map(&w.m_vt_l, w.vt_lo, (uint64_t)B * H * C_HID, Kp);
@@ -1642,14 +1681,17 @@ inline int tc_ipa_logits(TcWorkspace& w, const float* proj, float* L, int B, int
   return tc_launch_maps(w.m_pj_h, w.m_pj_l, w.m_pj_h, w.m_pj_l, w.m_pj_h, w.m_pj_l, p, st, launches);
 }
 
-// IPA o = a·v on the tensor cores (model/ipa_pytorch.py:433-436): per (sample, head) [N, 256] = a [N, N] · v [N, 256], K = N padded to a
-// multiple of 64 with zeros in both operands.  Output lands in feats[:, h*256 : (h+1)*256].
-inline int tc_ipa_av(TcWorkspace& w, const float* proj, const float* L, float* feats, int B, int N, int Np, cudaStream_t st, long long* launches) {
+// IPA o = a·v and o_pt = a·v_pts on the tensor cores (model/ipa_pytorch.py:433-447): per (sample, head) [N, 256] = a [N, N] · v [N, 256] and
+// [N, 36] = a · v_pts, K = N padded to a multiple of 64 with zeros in both operands.  Outputs: feats[:, h*256 : (h+1)*256] and optg.
+inline int tc_ipa_av(TcWorkspace& w, const float* proj, const float* vp, const float* L, float* feats, float* optg, int B, int N, int Np,
+                     cudaStream_t st, long long* launches) {
   const long long M = (long long)w.R * H;
   const long long n4 = M * (w.Kp / 4);
   split_pad_planes_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(L, Np, M, N, w.Kp, w.at_hi, w.at_lo);
-  vt_planes_kernel<<<dim3(w.Kp / 32, C_HID / 32, B * H), dim3(32, 8), 0, st>>>(proj, N, w.Kp, w.vt_hi, w.vt_lo);
-  if (launches) *launches += 2;
+  vt_planes_kernel<<<dim3(w.Kp / 32, C_HID / 32, B * H), dim3(32, 8), 0, st>>>(proj, PROJ_ALL, PROJ_Q + C_HID, 2 * C_HID, H, C_HID, C_HID, N, w.Kp,
+                                                                            w.vt_hi, w.vt_lo);
+  vt_planes_kernel<<<dim3(w.Kp / 32, 2, B * H), dim3(32, 8), 0, st>>>(vp, H * PV * 3, 0, PV * 3, H, PV * 3, 64, N, w.Kp, w.vp_hi, w.vp_lo);
+  if (launches) *launches += 3;
   TcGemmParams p{};
   p.M = N; p.N = C_HID; p.KB0 = w.Kp / TC_BK; p.KB1 = 0; p.planes = 2; p.epi = TC_EPI_F32;
   p.m_tiles = (N + TC_BM - 1) / TC_BM; p.nch = 2;
@@ -1657,6 +1699,44 @@ inline int tc_ipa_av(TcWorkspace& w, const float* proj, const float* L, float* f
   p.a_row_s0 = H * N; p.a_row_s1 = N; p.a_k_s1 = 0;
   p.b_row_s0 = H * C_HID; p.b_row_s1 = C_HID; p.b_k0 = 0; p.b_k_s1 = 0;
   p.n_valid = C_HID; p.out_f32 = feats; p.ldo = IPA_FEAT; p.o_s0 = (long long)N * IPA_FEAT; p.o_s1 = C_HID;
+  if (tc_launch_maps(w.m_at_h, w.m_at_l, w.m_at_h, w.m_at_l, w.m_vt_h, w.m_vt_l, p, st, launches)) return -2;
+  TcGemmParams q = p;   // points: 36 valid output columns per head (the 128-row weight box also covers the next head's rows; ignored)
+  q.N = 128; q.nch = 1; q.b_row_s0 = H * 64; q.b_row_s1 = 64;
+  q.n_valid = PV * 3; q.out_f32 = optg; q.ldo = H * PV * 3; q.o_s0 = (long long)N * H * PV * 3; q.o_s1 = PV * 3;
+  return tc_launch_maps(w.m_at_h, w.m_at_l, w.m_at_h, w.m_at_l, w.m_vp_h, w.m_vp_l, q, st, launches);
+}
+
+// Sequence-transformer self-attention (torch.nn.TransformerEncoderLayer inside model/ipa_pytorch.py:583-599) on the tensor cores.
+//   logits: S[b,h] = q_h·k_h^T / sqrt(80), K = 80 zero-padded to 128 per head;   values: y[:, h*80:(h+1)*80] = P[b,h]·v_h.
+inline int tc_tf_logits(TcWorkspace& w, const float* qkv, float* S, int B, int N, int Np, cudaStream_t st, long long* launches) {
+  const int W = 2 * TF_H * 128;
+  const long long n4 = (long long)w.R * (W / 4);
+  split_heads_pad_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(qkv, 3 * TF_D, w.R, 2 * TF_H, TF_DH, 128, w.pj_hi, w.pj_lo);
+  if (launches) ++*launches;
+  TcGemmParams p{};
+  p.M = N; p.N = 128; p.KB0 = 2; p.KB1 = 0; p.planes = 2; p.epi = TC_EPI_F32;
+  p.m_tiles = (N + TC_BM - 1) / TC_BM; p.nch = 1;
+  const int n_groups = (N + TC_NC - 1) / TC_NC;
+  p.bat_inner = TF_H; p.bat_tiles = p.m_tiles * n_groups; p.num_tiles = B * TF_H * p.bat_tiles;
+  p.a_row_s0 = N; p.a_row_s1 = 0; p.a_k_s1 = 128;
+  p.b_row_s0 = N; p.b_row_s1 = 0; p.b_k0 = TF_H * 128; p.b_k_s1 = 128;
+  p.n_valid = N; p.out_f32 = S; p.ldo = Np; p.o_s0 = (long long)TF_H * N * Np; p.o_s1 = (long long)N * Np;
+  p.alpha = (float)(1.0 / sqrt((double)TF_DH));
+  return tc_launch_maps(w.m_tq_h, w.m_tq_l, w.m_tq_h, w.m_tq_l, w.m_tq_h, w.m_tq_l, p, st, launches);
+}
+inline int tc_tf_values(TcWorkspace& w, const float* qkv, const float* S, float* y, int B, int N, int Np, cudaStream_t st, long long* launches) {
+  const long long M = (long long)w.R * TF_H;
+  const long long n4 = M * (w.Kp / 4);
+  split_pad_planes_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(S, Np, M, N, w.Kp, w.at_hi, w.at_lo);
+  vt_planes_kernel<<<dim3(w.Kp / 32, 4, B * TF_H), dim3(32, 8), 0, st>>>(qkv, 3 * TF_D, 2 * TF_D, TF_DH, TF_H, TF_DH, 128, N, w.Kp, w.vt_hi, w.vt_lo);
+  if (launches) *launches += 2;
+  TcGemmParams p{};
+  p.M = N; p.N = 128; p.KB0 = w.Kp / TC_BK; p.KB1 = 0; p.planes = 2; p.epi = TC_EPI_F32;
+  p.m_tiles = (N + TC_BM - 1) / TC_BM; p.nch = 1;
+  p.bat_inner = TF_H; p.bat_tiles = p.m_tiles; p.num_tiles = B * TF_H * p.bat_tiles;
+  p.a_row_s0 = TF_H * N; p.a_row_s1 = N; p.a_k_s1 = 0;
+  p.b_row_s0 = TF_H * 128; p.b_row_s1 = 128; p.b_k0 = 0; p.b_k_s1 = 0;
+  p.n_valid = TF_DH; p.out_f32 = y; p.ldo = TF_D; p.o_s0 = (long long)N * TF_D; p.o_s1 = TF_DH;
   return tc_launch_maps(w.m_at_h, w.m_at_l, w.m_at_h, w.m_at_l, w.m_vt_h, w.m_vt_l, p, st, launches);
 }
 
