@@ -59,7 +59,7 @@ struct Workspace {
   int B = 0, N = 0, Np = 0;
   long long rows = 0, edges = 0, chunk = 0;
   char* base = nullptr; size_t bytes = 0;
-  float *node_in, *temb, *AC, *node0, *node, *tmpA, *tmpB, *x320, *x320b, *qkv, *S, *y320, *ff, *proj, *qp, *kp, *vp, *optg,
+  float *node_in, *temb, *AC, *node0, *node, *tmpA, *tmpB, *x320, *x320b, *qkv, *S, *y320, *ff, *proj, *qp, *kp, *vp, *optg, *zbar,
       *L, *feats, *quat, *trans, *nb, *pquv, *z, *h1, *h2, *ychunk, *tors;
   // tensor-core path: bf16 hi/lo planes of z and staging
   TcWorkspace tc;
@@ -345,6 +345,14 @@ extern "C" int fd_load_weights(fd_handle h, const float* const* P) {
       const size_t owd = put(&X.WdT, nullptr, 128 * 32);
       for (int d = 0; d < 32; ++d) for (int c = 0; c < 128; ++c) pk.at(owd)[c * 32 + d] = wd[d * 128 + c];
       put(&X.bd, M.at(ip + "down_z.bias"), 32);
+      // block-diagonal image: o_pair[(h,d)] = sum_c Wd[d][c] zbar[(h,c)] for all heads in one GEMM (K = H*128, N = H*32)
+      const size_t obd = put(&X.down_bd.w, nullptr, (size_t)(H * 32) * (H * C_Z)), obb = put(&X.down_bd.b, nullptr, H * 32);
+      const float* bdz = M.at(ip + "down_z.bias");
+      for (int hh = 0; hh < H; ++hh)
+        for (int d = 0; d < 32; ++d) {
+          memcpy(pk.at(obd) + (size_t)(hh * 32 + d) * (H * C_Z) + hh * C_Z, wd + d * C_Z, C_Z * sizeof(float));
+          pk.at(obb)[hh * 32 + d] = bdz[d];
+        }
     }
     lin(X.out, ip + "linear_out", C_S, IPA_FEAT);
     lnp(X.ipa_ln, t + "ipa_ln_" + sb, C_S);
@@ -410,7 +418,7 @@ extern "C" int fd_load_weights(fd_handle h, const float* const* P) {
     reg(W.ne2, 256, 256); reg(W.ne4, 256, 256);
     for (int b = 0; b < NBLK; ++b) {
       const BlockW& X = W.blk[b];
-      reg(X.proj, PROJ_ALL, C_S); reg(X.out, C_S, IPA_FEAT);
+      reg(X.proj, PROJ_ALL, C_S); reg(X.out, C_S, IPA_FEAT); reg(X.down_bd, H * 32, H * C_Z);
       for (int l = 0; l < TF_LAYERS; ++l) {
         reg(X.tf[l].in_proj, 3 * TF_D, TF_D); reg(X.tf[l].out_proj, TF_D, TF_D); reg(X.tf[l].lin1, TF_D, TF_D); reg(X.tf[l].lin2, TF_D, TF_D);
       }
@@ -445,7 +453,7 @@ static int ensure_ws(fd_context* h, int B, int N) {
       {&w.node_in, R * NODE_IN_PAD}, {&w.temb, (size_t)B * 32}, {&w.AC, R * 256}, {&w.node0, R * C_S}, {&w.node, R * C_S},
       {&w.tmpA, R * C_S}, {&w.tmpB, R * C_S}, {&w.x320, R * TF_D}, {&w.x320b, R * TF_D}, {&w.qkv, R * 3 * TF_D},
       {&w.S, (size_t)B * TF_H * N * w.Np}, {&w.y320, R * TF_D}, {&w.ff, R * TF_D}, {&w.proj, R * PROJ_ALL},
-      {&w.qp, R * H * PQ * 3}, {&w.kp, R * H * PQ * 3}, {&w.vp, R * H * PV * 3}, {&w.optg, R * H * PV * 3},
+      {&w.qp, R * H * PQ * 3}, {&w.kp, R * H * PQ * 3}, {&w.vp, R * H * PV * 3}, {&w.optg, R * H * PV * 3}, {&w.zbar, tc ? R * H * C_Z : 0},
       {&w.L, (size_t)B * H * N * w.Np}, {&w.feats, R * IPA_FEAT}, {&w.quat, R * 4}, {&w.trans, R * 3}, {&w.nb, R * C_Z},
       {&w.pquv, R * ET_NODE}, {&w.z, (size_t)w.edges * C_Z}, {&w.tors, R * C_S},
       {&w.h1, tc ? 0 : (size_t)w.chunk * ET_HID}, {&w.h2, tc ? 0 : (size_t)w.chunk * ET_HID},
@@ -607,7 +615,7 @@ static int forward_impl(fd_context* h, int B, int N, const float* rigids_t, cons
     lc.end();
     lc.begin(ST_IPA_LOGITS);
     if (tc) {
-      if (!f.err && tc_ipa_logits(w.tc, w.proj, w.L, B, N, Np, (float)sqrt(1.0 / (3 * C_HID)), st, &h->launches))
+      if (!f.err && tc_ipa_logits(w.tc, w.proj, w.qp, w.kp, X.gamma, w.L, B, N, Np, (float)sqrt(1.0 / (3 * C_HID)), st, &h->launches))
         f.err = fail(FD_ECUDA, "ipa_logits (tensor-core) launch failed: %s", cudaGetErrorString(cudaGetLastError()));
     } else {
       GemmArgs g;
@@ -622,8 +630,10 @@ static int forward_impl(fd_context* h, int B, int N, const float* rigids_t, cons
     if (!f.err) {
       const size_t smem = (size_t)(H * Np + H * PQ * 3 + 2 * H * C_Z) * sizeof(float);
       if (tc) {
-        if (tc_ipa_edge(h->tcw, w.tc, b, w.L, w.qp, w.kp, res_mask, X.bb, X.gamma, X.WdT, X.bd, w.feats, B, N, Np, h->precision, st, &h->launches))
+        const bool one_kernel = tc_ipa_edge_fused_ok(N);
+        if (tc_ipa_edge(h->tcw, w.tc, b, w.L, w.qp, w.kp, res_mask, X.Wb, X.bb, X.gamma, X.WdT, X.bd, w.feats, w.zbar, B, N, Np, h->precision, st, &h->launches))
           f.err = fail(FD_ECUDA, "ipa_edge (planes) launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+        if (one_kernel) f.linear(w.zbar, H * C_Z, X.down_bd, H * C_Z, H * 32, w.feats + (H * C_HID + 4 * H * PV), IPA_FEAT, R);   // o_pair
       } else {
         ZRef zr; zr.f32 = w.z;
         ipa_edge_kernel<0><<<dim3(N, B), 256, smem, st>>>(zr, w.L, w.qp, w.kp, res_mask, X.Wb, X.bb, X.gamma, X.WdT, X.bd, w.feats, N, Np);

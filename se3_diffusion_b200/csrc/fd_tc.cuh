@@ -660,6 +660,7 @@ struct FuRing {
   }
 };
 
+constexpr int TC_QKV = PROJ_Q + PROJ_KV;   // q | k,v columns of the fused IPA projection (2048 + 4096); also the width of the logits operand planes
 constexpr int FU_THREADS = 320;   // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two groups of four)
 constexpr int FU_RING_BYTES = 128 * 1024;
 constexpr size_t FU_SMEM_BYTES = 64 * 1024 + FU_RING_BYTES + 512 + 2048 + 8 * 4096;   // + LayerNorm statistics + 8 x 4 KB store staging   // dynamic smem starts 1024-aligned (no static smem here)
@@ -1316,6 +1317,69 @@ __global__ void split_heads_pad_kernel(const float* __restrict__ x, int ld, long
   *reinterpret_cast<uint2*>(lo + m * W + k) = make_uint2(l0, l1);
 }
 
+// Operand planes of the extended IPA logits GEMM (model/ipa_pytorch.py:376-417).  Per head the contraction runs over 384 columns:
+//   [0,256)    scalar q_h / k_h
+//   [256,384)  point term  -½γ_h Σ|qp_i - kp_j|² = γ_h qp_i·kp_j - ½γ_h|kp_j|² - ½γ_h|qp_i|²  (the last addend is constant over j: it cancels in
+//              the softmax and is dropped).  The GEMM scales its accumulator by alpha, so the query side carries s = γ_h/alpha.  With
+//              x = x0 + x1 + x2 (three bf16 pieces, 24 bits) and the GEMM's split product (hi·hi + hi·lo + lo·hi) the columns are
+//                 +0..23  A (a0, a1)  B (k0, k1)      a0k0 + a0k1 + a1k0        (a = s·qp)
+//                +24..47  A (a0, 0)   B (k2, 0)       a0k2
+//                +48..71  A (a2, 0)   B (k0, 0)       a2k0
+//                +72..95  A (a1, 0)   B (k1, 0)       a1k1
+//                +96..98  A (1, 0)    B (n0|n1|n2, 0) n = -(s/2)|kp_j|²  exact to 24 bits
+//              i.e. every product term down to 2^-24, the accuracy of the fp32 reference loop.
+// Layout [R, 6144]: query side at column h*384, key side at 3072 + h*384.
+__global__ void __launch_bounds__(256) ipa_qkx_planes_kernel(const float* __restrict__ proj, const float* __restrict__ qp, const float* __restrict__ kp,
+                                                             const float* __restrict__ gamma, float inv_alpha, __nv_bfloat16* __restrict__ hi,
+                                                             __nv_bfloat16* __restrict__ lo) {
+  const long long row = blockIdx.x;
+  const int tid = threadIdx.x;
+  const float* pr = proj + row * PROJ_ALL;
+  __nv_bfloat16* oh = hi + row * TC_QKV; __nv_bfloat16* ol = lo + row * TC_QKV;
+#pragma unroll
+  for (int h = 0; h < H; ++h) {
+    __nv_bfloat16 a, b2;
+    split_bf16(pr[h * C_HID + tid], a, b2);
+    oh[h * 384 + tid] = a; ol[h * 384 + tid] = b2;
+    split_bf16(pr[PROJ_Q + h * 2 * C_HID + tid], a, b2);
+    oh[3072 + h * 384 + tid] = a; ol[3072 + h * 384 + tid] = b2;
+  }
+  const __nv_bfloat16 zero = __float2bfloat16(0.f);
+  for (int idx = tid; idx < 2 * H * 128; idx += 256) {
+    const int side = idx >> 10, h = (idx >> 7) & 7, e = idx & 127;      // side 0: query (A operand), 1: key (B operand)
+    const float s = gamma[h] * inv_alpha;
+    __nv_bfloat16 vh = zero, vl = zero;
+    if (e < 96) {
+      const int grp = e / 24, c = e - grp * 24;
+      const float x = side == 0 ? s * qp[row * (H * PQ * 3) + h * (PQ * 3) + c] : kp[row * (H * PQ * 3) + h * (PQ * 3) + c];
+      const __nv_bfloat16 x0 = __float2bfloat16(x);
+      const float r1 = x - __bfloat162float(x0);
+      const __nv_bfloat16 x1 = __float2bfloat16(r1);
+      const __nv_bfloat16 x2 = __float2bfloat16(r1 - __bfloat162float(x1));
+      if (side == 0) {
+        if (grp == 0) { vh = x0; vl = x1; } else if (grp == 1) vh = x0; else if (grp == 2) vh = x2; else vh = x1;
+      } else {
+        if (grp == 0) { vh = x0; vl = x1; } else if (grp == 1) vh = x2; else if (grp == 2) vh = x0; else vh = x1;
+      }
+    } else if (e < 99) {
+      if (side == 0) {
+        vh = __float2bfloat16(1.f);
+      } else {
+        float n2 = 0.f;
+#pragma unroll
+        for (int c = 0; c < PQ * 3; ++c) { const float k = kp[row * (H * PQ * 3) + h * (PQ * 3) + c]; n2 = fmaf(k, k, n2); }
+        const float n = -0.5f * s * n2;
+        const __nv_bfloat16 n0 = __float2bfloat16(n);
+        const float r1 = n - __bfloat162float(n0);
+        const __nv_bfloat16 n1 = __float2bfloat16(r1);
+        const __nv_bfloat16 n2b = __float2bfloat16(r1 - __bfloat162float(n1));
+        vh = e == 96 ? n0 : (e == 97 ? n1 : n2b);
+      }
+    }
+    oh[side * 3072 + h * 384 + 256 + e] = vh; ol[side * 3072 + h * 384 + 256 + e] = vl;
+  }
+}
+
 // planes -> fp32 (debug taps / export)
 __global__ void planes_to_f32_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo, float* __restrict__ out,
                                      long long n) {
@@ -1333,10 +1397,197 @@ static PFN_encodeTiled g_encode = nullptr;
 static int g_tc_sms = 148;
 
 static long long* g_tc_prof = nullptr;   // device [32]; set by fd_debug_tc_profile
+// ------------------------------------------------------------------------------------------------------------------
+// IPA edge pass, one kernel per block (model/ipa_pytorch.py:376-432): one CTA per query residue (b,i), 8 warps, mma.sync m16n8k16
+// with operand fragments built straight from global memory (no shared-memory staging of z):
+//   pass A  pair bias  pb[j][h] = z[j,:]·Wb[h,:].  A = z tile (16 edges x 128 channels); the contraction order over channels is free, so
+//           lane (g,t) takes the 64 contiguous bytes [32t, 32t+32) of rows g and g+8 and k-step ks uses channels 32t + 4ks + {0..3};
+//           the Wb fragments use the same channel permutation.  4-term split product (hi·hi + hi·lo + lo·hi + lo·lo).
+//   logits  lg[h][j] = L_in + sqrt(1/3)(pb + bb) + mask, where L_in = qk - ½γ_h Σ_p|qp_i - kp_j|² (up to a per-i constant) comes from the
+//           extended-K logits GEMM (tc_ipa_logits);  softmax over j;  probabilities -> L (for a·v) and smem
+//   pass B  zbar[h][c] = Σ_j a[h][j] z[j][c].  A = probabilities (heads as rows 0..7), B needs pairs along j: lane (g,t) loads 16 bytes
+//           (8 channels) of rows 2t, 2t+1, 2t+8, 2t+9 and interleaves them with byte permutes; warp w owns channels [64(w&1), +64)
+//           and the (w>>1)-th quarter of the edges; the four partial sums meet in shared memory.  The second read of z hits L2.
+//   zbar -> global; o_pair = Wd·zbar + bd is one block-diagonal tensor-core linear over all heads (caller)
+// The separate pair-bias GEMM + attention kernel (ipa_edge2) remain as the cross-check path (FD_IPA_EDGE2=1).
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+  uint32_t r;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel));
+  return r;
+}
+
+constexpr int E3_ASTRIDE = 528;   // bytes per head row of the probability planes (<= 256 bf16 = 512 B, + 16 B: conflict-free 4-byte reads)
+inline size_t ipa_edge3_smem(int Np) {
+  return (size_t)H * Np * 4 + 2 * (size_t)H * E3_ASTRIDE + 4 * (size_t)H * C_Z * 4 + 2 * 8 * 32 * 8;
+}
+
+template <int PLANES>
+__global__ void __launch_bounds__(256, 3) ipa_edge3_kernel(
+    const __nv_bfloat16* __restrict__ z_hi, const __nv_bfloat16* __restrict__ z_lo, float* __restrict__ L, const float* __restrict__ res_mask,
+    const float* __restrict__ Wb, const float* __restrict__ bb, float* __restrict__ zbar, int N, int Np) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const int NT = (N + 15) / 16;
+  float* lg = reinterpret_cast<float*>(smem_raw);                                 // [H][Np] logits -> probabilities
+  uint8_t* ap = smem_raw + (size_t)H * Np * 4;                                    // probability planes [2][H] rows of E3_ASTRIDE bytes
+  float* zbp = reinterpret_cast<float*>(ap + 2 * H * E3_ASTRIDE);                 // [4 edge quarters][H][128] partial zbar
+  uint2* wbs = reinterpret_cast<uint2*>(reinterpret_cast<uint8_t*>(zbp) + 4 * H * C_Z * 4);   // Wb fragments [plane][ks][lane]
+
+  const int i = blockIdx.x, b = blockIdx.y;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const long long rowi = (long long)b * N + i;
+  const long long zrow = rowi * N;                // first edge row of this residue in the z planes
+  {  // Wb fragments of k-step ks = warp (all warps together cover the 8 k-steps): channels 32t + 4ks + {0,1} and {2,3} of head g
+    const float4 w4 = *reinterpret_cast<const float4*>(Wb + g * C_Z + 32 * t + 4 * warp);
+    uint32_t h0, l0, h1, l1;
+    split2_bf16(w4.x, w4.y, h0, l0);
+    split2_bf16(w4.z, w4.w, h1, l1);
+    wbs[(0 * 8 + warp) * 32 + lane] = make_uint2(h0, h1);
+    wbs[(1 * 8 + warp) * 32 + lane] = make_uint2(l0, l1);
+  }
+  const float mi = res_mask[rowi];
+  // ---- phase 1: logits from the GEMM (scalar q·k and the point-distance term, see tc_ipa_logits) + mask -> lg ----
+  for (int idx = tid; idx < H * Np; idx += 256) {
+    const int h = idx / Np, j = idx - h * Np;
+    lg[idx] = j < N ? L[(((long long)b * H + h) * N + i) * Np + j] + 1e5f * (mi * res_mask[(long long)b * N + j] - 1.f) : 0.f;
+  }
+  __syncthreads();
+  // ---- pass A: pair bias on the tensor cores, added into lg ----
+  for (int jt = warp; jt < NT; jt += 8) {
+    const int r0 = jt * 16 + g, r1 = r0 + 8;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {     // channels 32t + [16 half, 16 half + 16): k-steps 4 half .. 4 half + 3
+      uint4 x0h[2], x1h[2], x0l[2], x1l[2];
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const long long o0 = (zrow + r0) * C_Z + 32 * t + 16 * half + 8 * q, o1 = (zrow + r1) * C_Z + 32 * t + 16 * half + 8 * q;
+        x0h[q] = r0 < N ? *reinterpret_cast<const uint4*>(z_hi + o0) : make_uint4(0u, 0u, 0u, 0u);
+        x1h[q] = r1 < N ? *reinterpret_cast<const uint4*>(z_hi + o1) : make_uint4(0u, 0u, 0u, 0u);
+        if (PLANES == 2) {
+          x0l[q] = r0 < N ? *reinterpret_cast<const uint4*>(z_lo + o0) : make_uint4(0u, 0u, 0u, 0u);
+          x1l[q] = r1 < N ? *reinterpret_cast<const uint4*>(z_lo + o1) : make_uint4(0u, 0u, 0u, 0u);
+        }
+      }
+#pragma unroll
+      for (int k4 = 0; k4 < 4; ++k4) {
+        const int ks = half * 4 + k4;
+        const uint2 bh = wbs[(0 * 8 + ks) * 32 + lane], bl = wbs[(1 * 8 + ks) * 32 + lane];
+        const uint4 v0h = x0h[k4 >> 1], v1h = x1h[k4 >> 1];
+        const uint32_t a0 = (k4 & 1) ? v0h.z : v0h.x, a2 = (k4 & 1) ? v0h.w : v0h.y;
+        const uint32_t a1 = (k4 & 1) ? v1h.z : v1h.x, a3 = (k4 & 1) ? v1h.w : v1h.y;
+        mma_bf16_16816(acc, a0, a1, a2, a3, bh.x, bh.y);
+        mma_bf16_16816(acc, a0, a1, a2, a3, bl.x, bl.y);
+        if (PLANES == 2) {
+          const uint4 v0l = x0l[k4 >> 1], v1l = x1l[k4 >> 1];
+          const uint32_t c0 = (k4 & 1) ? v0l.z : v0l.x, c2 = (k4 & 1) ? v0l.w : v0l.y;
+          const uint32_t c1 = (k4 & 1) ? v1l.z : v1l.x, c3 = (k4 & 1) ? v1l.w : v1l.y;
+          mma_bf16_16816(acc, c0, c1, c2, c3, bh.x, bh.y);
+          mma_bf16_16816(acc, c0, c1, c2, c3, bl.x, bl.y);
+        }
+      }
+    }
+    const int h0 = 2 * t, h1 = 2 * t + 1;
+    const float b0 = bb[h0], b1 = bb[h1];
+    if (r0 < N) { lg[h0 * Np + r0] += 0.57735026918962576f * (acc[0] + b0); lg[h1 * Np + r0] += 0.57735026918962576f * (acc[1] + b1); }
+    if (r1 < N) { lg[h0 * Np + r1] += 0.57735026918962576f * (acc[2] + b0); lg[h1 * Np + r1] += 0.57735026918962576f * (acc[3] + b1); }
+  }
+  __syncthreads();
+  // ---- softmax over j (warp <-> head); probabilities to L (fp32, for a·v) and to the bf16 hi/lo planes of pass B ----
+  {
+    float* row = lg + warp * Np;
+    float mx = -INFINITY;
+    for (int j = lane; j < N; j += 32) mx = fmaxf(mx, row[j]);
+    mx = warp_max(mx);
+    float sum = 0.f;
+    for (int j = lane; j < N; j += 32) { const float e = expf(row[j] - mx); row[j] = e; sum += e; }
+    sum = warp_sum(sum);
+    const float inv = 1.f / sum;
+    float* Lrow = L + (((long long)b * H + warp) * N + i) * Np;
+    __nv_bfloat16* ph = reinterpret_cast<__nv_bfloat16*>(ap + warp * E3_ASTRIDE);
+    __nv_bfloat16* pl = reinterpret_cast<__nv_bfloat16*>(ap + (H + warp) * E3_ASTRIDE);
+    const int Jp = NT * 16 > Np ? NT * 16 : Np;
+    for (int j = lane; j < Jp; j += 32) {
+      const float a = j < N ? row[j] * inv : 0.f;
+      if (j < Np) Lrow[j] = a;
+      if (j < NT * 16) { __nv_bfloat16 hh, ll; split_bf16(a, hh, ll); ph[j] = hh; pl[j] = ll; }
+    }
+  }
+  __syncthreads();
+  // ---- pass B: zbar partials.  n-tile x (0..7), column n  <->  channel 64 ch + 8 n + x ----
+  {
+    const int ch = warp & 1, kq = warp >> 1;
+    const int KQ = (NT + 3) / 4;
+    const int ks_end = (kq + 1) * KQ < NT ? (kq + 1) * KQ : NT;
+    float acc[8][4];
+#pragma unroll
+    for (int x = 0; x < 8; ++x) { acc[x][0] = 0.f; acc[x][1] = 0.f; acc[x][2] = 0.f; acc[x][3] = 0.f; }
+    const int cb = 64 * ch + 8 * g;
+    for (int ks = kq * KQ; ks < ks_end; ++ks) {
+      const int ja = ks * 16 + 2 * t;
+      uint4 wh[4], wl[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int j = ja + (q & 1) + (q >> 1) * 8;     // rows 2t, 2t+1, 2t+8, 2t+9
+        const long long o = (zrow + j) * C_Z + cb;
+        wh[q] = j < N ? *reinterpret_cast<const uint4*>(z_hi + o) : make_uint4(0u, 0u, 0u, 0u);
+        if (PLANES == 2) wl[q] = j < N ? *reinterpret_cast<const uint4*>(z_lo + o) : make_uint4(0u, 0u, 0u, 0u);
+      }
+      // probabilities: head g, edges ja, ja+1 (a0) and ja+8, ja+9 (a2); MMA rows 8..15 are zero
+      const uint32_t ah0 = *reinterpret_cast<const uint32_t*>(ap + g * E3_ASTRIDE + ja * 2);
+      const uint32_t ah2 = *reinterpret_cast<const uint32_t*>(ap + g * E3_ASTRIDE + (ja + 8) * 2);
+      const uint32_t al0 = *reinterpret_cast<const uint32_t*>(ap + (H + g) * E3_ASTRIDE + ja * 2);
+      const uint32_t al2 = *reinterpret_cast<const uint32_t*>(ap + (H + g) * E3_ASTRIDE + (ja + 8) * 2);
+      const uint32_t w0h[4] = {wh[0].x, wh[0].y, wh[0].z, wh[0].w}, w1h[4] = {wh[1].x, wh[1].y, wh[1].z, wh[1].w};
+      const uint32_t w2h[4] = {wh[2].x, wh[2].y, wh[2].z, wh[2].w}, w3h[4] = {wh[3].x, wh[3].y, wh[3].z, wh[3].w};
+#pragma unroll
+      for (int x = 0; x < 8; ++x) {
+        const uint32_t sel = (x & 1) ? 0x7632u : 0x5410u;
+        const uint32_t b0 = prmt(w0h[x >> 1], w1h[x >> 1], sel), b1 = prmt(w2h[x >> 1], w3h[x >> 1], sel);
+        mma_bf16_16816(acc[x], ah0, 0u, ah2, 0u, b0, b1);
+        mma_bf16_16816(acc[x], al0, 0u, al2, 0u, b0, b1);
+      }
+      if (PLANES == 2) {
+        const uint32_t w0l[4] = {wl[0].x, wl[0].y, wl[0].z, wl[0].w}, w1l[4] = {wl[1].x, wl[1].y, wl[1].z, wl[1].w};
+        const uint32_t w2l[4] = {wl[2].x, wl[2].y, wl[2].z, wl[2].w}, w3l[4] = {wl[3].x, wl[3].y, wl[3].z, wl[3].w};
+#pragma unroll
+        for (int x = 0; x < 8; ++x) {
+          const uint32_t sel = (x & 1) ? 0x7632u : 0x5410u;
+          const uint32_t b0 = prmt(w0l[x >> 1], w1l[x >> 1], sel), b1 = prmt(w2l[x >> 1], w3l[x >> 1], sel);
+          mma_bf16_16816(acc[x], ah0, 0u, ah2, 0u, b0, b1);
+        }
+      }
+    }
+    // C rows g = head, columns 2t and 2t+1 of n-tile x  ->  channels 64 ch + 16 t + x and 64 ch + 16 t + 8 + x
+    float* dst = zbp + ((size_t)kq * H + g) * C_Z + 64 * ch + 16 * t;
+#pragma unroll
+    for (int x = 0; x < 8; ++x) { dst[x] = acc[x][0]; dst[8 + x] = acc[x][1]; }
+  }
+  __syncthreads();
+  {  // zbar = sum of the four edge-quarter partials -> global [B*N, H*128]; o_pair = Wd·zbar + bd follows as one block-diagonal GEMM
+    const int h = tid >> 5, c4 = (tid & 31) * 4;
+    const float* z0 = zbp + h * C_Z + c4;
+    const float4 p0 = *reinterpret_cast<const float4*>(z0), p1 = *reinterpret_cast<const float4*>(z0 + H * C_Z);
+    const float4 p2 = *reinterpret_cast<const float4*>(z0 + 2 * H * C_Z), p3 = *reinterpret_cast<const float4*>(z0 + 3 * H * C_Z);
+    *reinterpret_cast<float4*>(zbar + rowi * (H * C_Z) + h * C_Z + c4) =
+        make_float4((p0.x + p1.x) + (p2.x + p3.x), (p0.y + p1.y) + (p2.y + p3.y), (p0.z + p1.z) + (p2.z + p3.z), (p0.w + p1.w) + (p2.w + p3.w));
+  }
+}
+
+static int g_tc_edge3 = 1;   // FD_IPA_EDGE2=1 selects the two-kernel path (pair-bias GEMM + attention kernel) kept as the cross-check
 static int g_tc_fused = 1;   // FD_TC_UNFUSED=1 selects the three-launch path (kept as the fused kernel's cross-check)
 inline int tc_init(int sm_count) {
   g_tc_sms = sm_count;
   g_tc_fused = getenv("FD_TC_UNFUSED") ? 0 : 1;
+  g_tc_edge3 = getenv("FD_IPA_EDGE2") ? 0 : 1;
+  if (cudaFuncSetAttribute(ipa_edge3_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ipa_edge3_smem(256)) != cudaSuccess) return -2;
+  if (cudaFuncSetAttribute(ipa_edge3_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ipa_edge3_smem(256)) != cudaSuccess) return -2;
   void* fn = nullptr;
   cudaDriverEntryPointQueryResult q;
   if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn) return -2;
@@ -1376,8 +1627,6 @@ struct TcWeights {
   TcMat w1z[3], w2[3], wf[3];     // EdgeTransition: [384][128], [384][384], [128][512] = [Wf | Wf[:, :128]]
   TcMat wb[4];                    // IPA linear_b padded to [128][128] (rows 0..7 real): pair bias z·Wb^T on the tensor cores (UMMA N = 16)
 };
-
-constexpr int TC_QKV = PROJ_Q + PROJ_KV;   // q | k,v columns of the fused IPA projection (2048 + 4096)
 
 struct TcWorkspace {
   char* base = nullptr;
@@ -1514,7 +1763,7 @@ inline int tc_bind_workspace(TcWorkspace& w, char* p, int B, int N) {
   rc |= tc_make_map(&w.m_pj_h, w.pj_hi, R, TC_QKV); rc |= tc_make_map(&w.m_pj_l, w.pj_lo, R, TC_QKV);
   rc |= tc_make_map(&w.m_at_h, w.at_hi, R * H, Kp); rc |= tc_make_map(&w.m_at_l, w.at_lo, R * H, Kp);
   rc |= tc_make_map(&w.m_vt_h, w.vt_hi, (uint64_t)B * H * C_HID, Kp); rc |= tc_make_map(&w.m_vt_l, w.vt_lo, (uint64_t)B * H * C_HID, Kp);
-  for (int K : {128, 256, 320, 384, IPA_FEAT}) {
+  for (int K : {128, 256, 320, 384, H * C_Z, IPA_FEAT}) {
     std::pair<CUtensorMap, CUtensorMap> mp;
     rc |= tc_make_map(&mp.first, w.a_hi, (uint64_t)w.R, (uint64_t)K);
     rc |= tc_make_map(&mp.second, w.a_lo, (uint64_t)w.R, (uint64_t)K);
@@ -1648,10 +1897,18 @@ inline void tc_export_z(TcWorkspace& w, float* z_f32, int prec, cudaStream_t st)
 
 // IPA edge pass in the tensor-core modes.  Pair bias  pbias[e,h] = z_e·Wb[h]^T + bb[h]  first, as a memory-bound tcgen05 GEMM over
 // the z planes (UMMA N = 16, 8 valid columns, fp32 out), then the attention kernel streams z exactly once (Σ_j a·z).
+inline bool tc_ipa_edge_fused_ok(int N) { return g_tc_edge3 && N <= 256; }
 inline int tc_ipa_edge(const TcWeights& tw, TcWorkspace& w, int blk, float* L, const float* qp, const float* kp, const float* res_mask,
-                       const float* bb, const float* gamma, const float* WdT, const float* bd, float* feats, int B, int N, int Np, int prec,
-                       cudaStream_t st, long long* launches) {
+                       const float* Wb, const float* bb, const float* gamma, const float* WdT, const float* bd, float* feats, float* zbar, int B,
+                       int N, int Np, int prec, cudaStream_t st, long long* launches) {
   const int planes = prec == 1 ? 2 : 1;
+  if (tc_ipa_edge_fused_ok(N)) {
+    const size_t smem = ipa_edge3_smem(Np);
+    if (prec == 1) ipa_edge3_kernel<2><<<dim3(N, B), 256, smem, st>>>(w.z_hi, w.z_lo, L, res_mask, Wb, bb, zbar, N, Np);
+    else ipa_edge3_kernel<1><<<dim3(N, B), 256, smem, st>>>(w.z_hi, w.z_lo, L, res_mask, Wb, bb, zbar, N, Np);
+    if (launches) ++*launches;
+    return cudaGetLastError() == cudaSuccess ? 0 : -2;
+  }
   TcGemmParams p{};
   p.M = (int)w.E; p.N = 128; p.KB0 = 2; p.KB1 = 0; p.planes = planes; p.epi = TC_EPI_F32; p.bias = bb; p.mma_n = 16; p.lolo = 1;
   p.m_tiles = (int)((w.E + TC_BM - 1) / TC_BM); p.nch = 1; p.num_tiles = p.m_tiles; p.n_valid = H; p.out_f32 = w.pbias; p.ldo = H;
@@ -1664,19 +1921,25 @@ inline int tc_ipa_edge(const TcWeights& tw, TcWorkspace& w, int blk, float* L, c
   return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 
-// IPA scalar attention logits on the tensor cores (model/ipa_pytorch.py:376-383): per (sample, head) a [N,N] = q·k^T GEMM with K = 256,
-// both operands from the split projection planes, scaled by sqrt(1/(3*c_hidden)), fp32 out into L [B,H,N,Np].
-inline int tc_ipa_logits(TcWorkspace& w, const float* proj, float* L, int B, int N, int Np, float alpha, cudaStream_t st, long long* launches) {
-  const long long n4 = (long long)w.R * (TC_QKV / 4);
-  split_planes_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(proj, PROJ_ALL, w.R, TC_QKV, w.pj_hi, w.pj_lo);
+// IPA attention logits on the tensor cores (model/ipa_pytorch.py:376-417): per (sample, head) a [N,N] = q·k^T GEMM, both operands from split
+// planes, scaled by sqrt(1/(3*c_hidden)), fp32 out into L [B,H,N,Np].  K = 256 (scalar part) or 384 with the point-distance columns.
+inline int tc_ipa_logits(TcWorkspace& w, const float* proj, const float* qp, const float* kp, const float* gamma, float* L, int B, int N, int Np,
+                         float alpha, cudaStream_t st, long long* launches) {
+  const bool ext = tc_ipa_edge_fused_ok(N);     // the one-kernel edge pass takes the point-distance term from this GEMM (K = 384 per head)
+  if (ext) {
+    ipa_qkx_planes_kernel<<<(unsigned)w.R, 256, 0, st>>>(proj, qp, kp, gamma, 1.f / alpha, w.pj_hi, w.pj_lo);
+  } else {
+    const long long n4 = (long long)w.R * (TC_QKV / 4);
+    split_planes_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(proj, PROJ_ALL, w.R, TC_QKV, w.pj_hi, w.pj_lo);
+  }
   if (launches) ++*launches;
   TcGemmParams p{};
-  p.M = N; p.N = 128; p.KB0 = C_HID / TC_BK; p.KB1 = 0; p.planes = 2; p.epi = TC_EPI_F32;
+  p.M = N; p.N = 128; p.KB0 = (ext ? 384 : C_HID) / TC_BK; p.KB1 = 0; p.planes = 2; p.epi = TC_EPI_F32;
   p.m_tiles = (N + TC_BM - 1) / TC_BM; p.nch = 1;
   const int n_groups = (N + TC_NC - 1) / TC_NC;
   p.bat_inner = H; p.bat_tiles = p.m_tiles * n_groups; p.num_tiles = B * H * p.bat_tiles;
-  p.a_row_s0 = N; p.a_row_s1 = 0; p.a_k_s1 = C_HID;
-  p.b_row_s0 = N; p.b_row_s1 = 0; p.b_k0 = PROJ_Q; p.b_k_s1 = 2 * C_HID;
+  p.a_row_s0 = N; p.a_row_s1 = 0; p.a_k_s1 = ext ? 384 : C_HID;
+  p.b_row_s0 = N; p.b_row_s1 = 0; p.b_k0 = ext ? 3072 : PROJ_Q; p.b_k_s1 = ext ? 384 : 2 * C_HID;
   p.n_valid = N; p.out_f32 = L; p.ldo = Np; p.o_s0 = (long long)H * N * Np; p.o_s1 = (long long)N * Np; p.alpha = alpha;
   return tc_launch_maps(w.m_pj_h, w.m_pj_l, w.m_pj_h, w.m_pj_l, w.m_pj_h, w.m_pj_l, p, st, launches);
 }

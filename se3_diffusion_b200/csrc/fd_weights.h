@@ -81,6 +81,7 @@ struct BlockW {
   const float* Wb = nullptr; const float* bb = nullptr;   // linear_b [8][128], [8]
   const float* gamma = nullptr;                           // softplus(head_weights)·sqrt(1/(3·PQ·9/2)) [8]
   const float* WdT = nullptr; const float* bd = nullptr;  // down_z transposed [128][32], [32]
+  Lin down_bd;                                            // down_z as one block-diagonal linear over all heads: [256][1024], bias [256] (tensor-core path)
   Lin out;                   // linear_out [256][2688]
   LNp ipa_ln;
   Lin skip;                  // [64][256]
