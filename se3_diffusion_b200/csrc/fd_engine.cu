@@ -180,6 +180,7 @@ extern "C" int fd_create(fd_handle* out, int device) {
   CK(cudaMemcpyToSymbol(c_time_freq, tf, sizeof(tf)));
   CK(cudaMemcpyToSymbol(c_idx_den, idn, sizeof(idn)));
   CK(cudaMemcpyToSymbol(c_dgram_lower, dl, sizeof(dl)));
+  CK(cudaMemcpyToSymbol(g_dgram_lower, dl, sizeof(dl)));
   CK(cudaMemcpyToSymbol(c_pi_f32, &pi, sizeof(pi)));
   // sigma grid + omega grid + cdf(t=1)
   h->h_sigma_grid.resize(SO3_NSIGMA);

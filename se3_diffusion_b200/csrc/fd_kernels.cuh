@@ -10,6 +10,7 @@ namespace fd {
 __constant__ float c_time_freq[16];
 __constant__ float c_idx_den[16];
 __constant__ float c_dgram_lower[NBINS];
+__device__ float g_dgram_lower[32];   // same edges in global memory for per-lane (non-uniform) reads; entries >= NBINS unused
 __constant__ float c_pi_f32;
 
 // Edge tensor storage.  fp32 mode: z [E,128] fp32.  Tensor-core modes: bf16 "hi" plane (+ "lo" plane = bf16(z - hi) in
@@ -280,6 +281,54 @@ __global__ void __launch_bounds__(256) edge_embed_l0_kernel(
     *reinterpret_cast<uint2*>(h_hi + r * 128 + lane * 4) = *reinterpret_cast<const uint2*>(hi);
     if (OMODE == 2) *reinterpret_cast<uint2*>(h_lo + r * 128 + lane * 4) = *reinterpret_cast<const uint2*>(lo);
   }
+}
+
+// Same layer for the tensor-core path over the whole edge tensor: grid (B*N query rows, ceil(N/8)), one warp per edge, no integer
+// divisions, and the distogram bin found by one ballot (lane k tests bin k) instead of a 22-step scan — the first version of this
+// kernel was instruction-issue-bound (68 warp instructions per edge, most of them index arithmetic).
+template <int OMODE>   // 1: bf16 hi plane; 2: hi + lo planes
+__global__ void __launch_bounds__(256) edge_embed_l0_rows_kernel(
+    const float* __restrict__ AC, const float* __restrict__ T, const float* __restrict__ D /* [NBINS+1][128] */,
+    const float* __restrict__ w0r, const int* __restrict__ seq_idx, const float* __restrict__ sc_ca,
+    __nv_bfloat16* __restrict__ h_hi, __nv_bfloat16* __restrict__ h_lo, int N) {
+  const int lane = threadIdx.x & 31;
+  const int j = blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (j >= N) return;
+  const long long ri = blockIdx.x;                        // b*N + i
+  const long long rj = ri - (ri % N) + j;                 // one 64-bit remainder per warp: b*N + j
+  const long long r = ri * N + j;                         // edge row
+  const float dx = sc_ca[ri * 3 + 0] - sc_ca[rj * 3 + 0];
+  const float dy = sc_ca[ri * 3 + 1] - sc_ca[rj * 3 + 1];
+  const float dz = sc_ca[ri * 3 + 2] - sc_ca[rj * 3 + 2];
+  const float dist = sqrtf(dx * dx + dy * dy + dz * dz);
+  const float lo_e = lane < NBINS ? __ldg(g_dgram_lower + lane) : 3e38f;
+  const float hi_e = lane + 1 < NBINS ? __ldg(g_dgram_lower + lane + 1) : 1e8f;
+  const unsigned hit = __ballot_sync(0xffffffffu, lane < NBINS && dist > lo_e && dist < hi_e);
+  const int bin = hit ? 31 - __clz(hit) : NBINS;          // bins are disjoint; the reference scan keeps the last match
+  const int d = seq_idx[ri] - seq_idx[rj];
+  const float4 a = reinterpret_cast<const float4*>(AC + ri * 256)[lane];
+  const float4 c = reinterpret_cast<const float4*>(AC + rj * 256 + 128)[lane];
+  const float4 dg = reinterpret_cast<const float4*>(D + bin * 128)[lane];
+  float4 tr;
+  if (d >= -REL_DMAX && d <= REL_DMAX) {
+    tr = reinterpret_cast<const float4*>(T + (long long)(d + REL_DMAX) * 128)[lane];
+  } else {  // out-of-table offset: evaluate the embedding on the fly
+    const int k = lane & 15;
+    const float ia = __fdiv_rn(__fmul_rn((float)d, c_pi_f32), c_idx_den[k]);
+    const float mine = lane < 16 ? sinf(ia) : cosf(ia);   // lane e holds emb[e]
+    tr = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int e = 0; e < 32; ++e) {
+      const float em = __shfl_sync(0xffffffffu, mine, e);
+      const float4 w = reinterpret_cast<const float4*>(w0r + e * 128)[lane];
+      tr.x = fmaf(w.x, em, tr.x); tr.y = fmaf(w.y, em, tr.y); tr.z = fmaf(w.z, em, tr.z); tr.w = fmaf(w.w, em, tr.w);
+    }
+  }
+  const float o0 = fmaxf(((a.x + c.x) + tr.x) + dg.x, 0.f), o1 = fmaxf(((a.y + c.y) + tr.y) + dg.y, 0.f);
+  const float o2 = fmaxf(((a.z + c.z) + tr.z) + dg.z, 0.f), o3 = fmaxf(((a.w + c.w) + tr.w) + dg.w, 0.f);
+  __nv_bfloat16 hi[4], lo[4];
+  split_bf16(o0, hi[0], lo[0]); split_bf16(o1, hi[1], lo[1]); split_bf16(o2, hi[2], lo[2]); split_bf16(o3, hi[3], lo[3]);
+  *reinterpret_cast<uint2*>(h_hi + r * 128 + lane * 4) = *reinterpret_cast<const uint2*>(hi);
+  if (OMODE == 2) *reinterpret_cast<uint2*>(h_lo + r * 128 + lane * 4) = *reinterpret_cast<const uint2*>(lo);
 }
 
 // ----------------------------------------------------------------------------------------------------------------

@@ -1803,8 +1803,9 @@ inline int tc_edge_embed(const TcWeights& tw, TcWorkspace& w, int prec, const fl
   const long long E = w.E;
   const int planes = prec == 1 ? 2 : 1;
   if (E > 0x7fffffffLL) return -1;
-  if (planes == 2) edge_embed_l0_kernel<2><<<(unsigned)((E + 7) / 8), 256, 0, st>>>(AC, T, D, w0r, seq_idx, sc_ca, nullptr, w.h1_hi, w.h1_lo, 0, E, N);
-  else edge_embed_l0_kernel<1><<<(unsigned)((E + 7) / 8), 256, 0, st>>>(AC, T, D, w0r, seq_idx, sc_ca, nullptr, w.h1_hi, w.h1_lo, 0, E, N);
+  const dim3 l0_grid((unsigned)w.R, (unsigned)((N + 7) / 8));
+  if (planes == 2) edge_embed_l0_rows_kernel<2><<<l0_grid, 256, 0, st>>>(AC, T, D, w0r, seq_idx, sc_ca, w.h1_hi, w.h1_lo, N);
+  else edge_embed_l0_rows_kernel<1><<<l0_grid, 256, 0, st>>>(AC, T, D, w0r, seq_idx, sc_ca, w.h1_hi, w.h1_lo, N);
   if (launches) ++*launches;
   if (g_tc_fused) {   // layers 2..4 in one persistent kernel (h1 stays in tensor memory)
     EmbedFusedParams f{};
