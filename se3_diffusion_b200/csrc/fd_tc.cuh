@@ -1401,8 +1401,9 @@ static long long* g_tc_prof = nullptr;   // device [32]; set by fd_debug_tc_prof
 // IPA edge pass, one kernel per block (model/ipa_pytorch.py:376-432): one CTA per query residue (b,i), 8 warps, mma.sync m16n8k16
 // with operand fragments built straight from global memory (no shared-memory staging of z):
 //   pass A  pair bias  pb[j][h] = z[j,:]·Wb[h,:].  A = z tile (16 edges x 128 channels); the contraction order over channels is free, so
-//           lane (g,t) takes the 64 contiguous bytes [32t, 32t+32) of rows g and g+8 and k-step ks uses channels 32t + 4ks + {0..3};
-//           the Wb fragments use the same channel permutation.  4-term split product (hi·hi + hi·lo + lo·hi + lo·lo).
+//           the q-th 16-byte load of lane (g,t) takes channels 32q + 8t + {0..7} of rows g and g+8 (a warp instruction reads 64 contiguous
+//           bytes of 8 rows, every sector fully used) and k-step ks = 2q + e uses channels 32q + 8t + 4e + {0..3}; the Wb fragments use
+//           the same channel permutation.  4-term split product (hi·hi + hi·lo + lo·hi + lo·lo).
 //   logits  lg[h][j] = L_in + sqrt(1/3)(pb + bb) + mask, where L_in = qk - ½γ_h Σ_p|qp_i - kp_j|² (up to a per-i constant) comes from the
 //           extended-K logits GEMM (tc_ipa_logits);  softmax over j;  probabilities -> L (for a·v) and smem
 //   pass B  zbar[h][c] = Σ_j a[h][j] z[j][c].  A = probabilities (heads as rows 0..7), B needs pairs along j: lane (g,t) loads 16 bytes
@@ -1443,8 +1444,8 @@ __global__ void __launch_bounds__(256, 3) ipa_edge3_kernel(
   const int g = lane >> 2, t = lane & 3;
   const long long rowi = (long long)b * N + i;
   const long long zrow = rowi * N;                // first edge row of this residue in the z planes
-  {  // Wb fragments of k-step ks = warp (all warps together cover the 8 k-steps): channels 32t + 4ks + {0,1} and {2,3} of head g
-    const float4 w4 = *reinterpret_cast<const float4*>(Wb + g * C_Z + 32 * t + 4 * warp);
+  {  // Wb fragments of k-step ks = warp (all warps together cover the 8 k-steps): channels 32(ks>>1) + 8t + 4(ks&1) + {0,1} and {2,3} of head g
+    const float4 w4 = *reinterpret_cast<const float4*>(Wb + g * C_Z + 32 * (warp >> 1) + 8 * t + 4 * (warp & 1));
     uint32_t h0, l0, h1, l1;
     split2_bf16(w4.x, w4.y, h0, l0);
     split2_bf16(w4.z, w4.w, h1, l1);
@@ -1463,11 +1464,11 @@ __global__ void __launch_bounds__(256, 3) ipa_edge3_kernel(
     const int r0 = jt * 16 + g, r1 = r0 + 8;
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-    for (int half = 0; half < 2; ++half) {     // channels 32t + [16 half, 16 half + 16): k-steps 4 half .. 4 half + 3
+    for (int half = 0; half < 2; ++half) {     // loads q = 2 half, 2 half + 1: k-steps 4 half .. 4 half + 3
       uint4 x0h[2], x1h[2], x0l[2], x1l[2];
 #pragma unroll
       for (int q = 0; q < 2; ++q) {
-        const long long o0 = (zrow + r0) * C_Z + 32 * t + 16 * half + 8 * q, o1 = (zrow + r1) * C_Z + 32 * t + 16 * half + 8 * q;
+        const long long o0 = (zrow + r0) * C_Z + 32 * (2 * half + q) + 8 * t, o1 = (zrow + r1) * C_Z + 32 * (2 * half + q) + 8 * t;
         x0h[q] = r0 < N ? *reinterpret_cast<const uint4*>(z_hi + o0) : make_uint4(0u, 0u, 0u, 0u);
         x1h[q] = r1 < N ? *reinterpret_cast<const uint4*>(z_hi + o1) : make_uint4(0u, 0u, 0u, 0u);
         if (PLANES == 2) {
