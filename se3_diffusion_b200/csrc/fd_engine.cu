@@ -632,7 +632,7 @@ static int forward_impl(fd_context* h, int B, int N, const float* rigids_t, cons
       const size_t smem = (size_t)(H * Np + H * PQ * 3 + 2 * H * C_Z) * sizeof(float);
       if (tc) {
         const bool one_kernel = tc_ipa_edge_fused_ok(N);
-        if (tc_ipa_edge(h->tcw, w.tc, b, w.L, w.qp, w.kp, res_mask, X.Wb, X.bb, X.gamma, X.WdT, X.bd, w.feats, w.zbar, B, N, Np, h->precision, st, &h->launches))
+        if (tc_ipa_edge(h->tcw, w.tc, b, w.L, w.qp, w.kp, res_mask, X.Wb, X.bb, X.gamma, X.WdT, X.bd, w.feats, w.zbar, B, N, Np, h->precision, h->debug ? 1 : 0, st, &h->launches))
           f.err = fail(FD_ECUDA, "ipa_edge (planes) launch failed: %s", cudaGetErrorString(cudaGetLastError()));
         if (one_kernel) f.linear(w.zbar, H * C_Z, X.down_bd, H * C_Z, H * 32, w.feats + (H * C_HID + 4 * H * PV), IPA_FEAT, R);   // o_pair
       } else {

@@ -1281,21 +1281,21 @@ __global__ void split_pad_planes_kernel(const float* __restrict__ x, int ld, lon
 //   vt[(bh*dhp + c), j] = x[(b*N + j)*ld + col0 + h*hstride + c]  for c < dh, j < N; zero elsewhere (c < dhp, j < Kp).
 __global__ void vt_planes_kernel(const float* __restrict__ x, int ld, int col0, int hstride, int nheads, int dh, int dhp, int N, int Kp,
                                  __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
-  __shared__ float tile[32][33];
+  __shared__ float tile[64][33];                  // 64 edges x 32 channels per block; Kp is a multiple of 64
   const int bh = blockIdx.z, b = bh / nheads, hh = bh - b * nheads;
-  const int j0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int j0 = blockIdx.x * 64, c0 = blockIdx.y * 32;
   const int tx = threadIdx.x, ty = threadIdx.y;   // 32 x 8
-  for (int r = ty; r < 32; r += 8) {
+  for (int r = ty; r < 64; r += 8) {
     const int j = j0 + r;
     tile[r][tx] = (j < N && c0 + tx < dh) ? x[((long long)b * N + j) * ld + col0 + hh * hstride + c0 + tx] : 0.f;
   }
   __syncthreads();
-  for (int r = ty; r < 32; r += 8) {
-    const float v = tile[tx][r];                  // (j = j0 + tx, c = c0 + r)
-    __nv_bfloat16 h, l;
-    split_bf16(v, h, l);
-    const long long o = ((long long)bh * dhp + c0 + r) * Kp + j0 + tx;
-    hi[o] = h; lo[o] = l;
+  for (int r = ty; r < 32; r += 8) {              // channel c0 + r: lane tx writes the edge pair (j0 + 2 tx, j0 + 2 tx + 1)
+    uint32_t h2, l2;
+    split2_bf16(tile[2 * tx][r], tile[2 * tx + 1][r], h2, l2);
+    const long long o = ((long long)bh * dhp + c0 + r) * Kp + j0 + 2 * tx;
+    *reinterpret_cast<uint32_t*>(hi + o) = h2;
+    *reinterpret_cast<uint32_t*>(lo + o) = l2;
   }
 }
 
@@ -1431,7 +1431,8 @@ inline size_t ipa_edge3_smem(int Np) {
 template <int PLANES>
 __global__ void __launch_bounds__(256, 3) ipa_edge3_kernel(
     const __nv_bfloat16* __restrict__ z_hi, const __nv_bfloat16* __restrict__ z_lo, float* __restrict__ L, const float* __restrict__ res_mask,
-    const float* __restrict__ Wb, const float* __restrict__ bb, float* __restrict__ zbar, int N, int Np) {
+    const float* __restrict__ Wb, const float* __restrict__ bb, float* __restrict__ zbar, __nv_bfloat16* __restrict__ at_hi,
+    __nv_bfloat16* __restrict__ at_lo, int Kp, int write_L, int N, int Np) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const int NT = (N + 15) / 16;
   float* lg = reinterpret_cast<float*>(smem_raw);                                 // [H][Np] logits -> probabilities
@@ -1510,14 +1511,20 @@ __global__ void __launch_bounds__(256, 3) ipa_edge3_kernel(
     for (int j = lane; j < N; j += 32) { const float e = expf(row[j] - mx); row[j] = e; sum += e; }
     sum = warp_sum(sum);
     const float inv = 1.f / sum;
+    // two adjacent edges per lane: probabilities go (a) to the smem planes of pass B, (b) to the global [B*H*N, Kp] bf16 hi/lo planes the
+    // a·v GEMMs read as their A operand (zero-padded to Kp), (c) as fp32 to L only when the debug tap wants them
     float* Lrow = L + (((long long)b * H + warp) * N + i) * Np;
-    __nv_bfloat16* ph = reinterpret_cast<__nv_bfloat16*>(ap + warp * E3_ASTRIDE);
-    __nv_bfloat16* pl = reinterpret_cast<__nv_bfloat16*>(ap + (H + warp) * E3_ASTRIDE);
-    const int Jp = NT * 16 > Np ? NT * 16 : Np;
-    for (int j = lane; j < Jp; j += 32) {
-      const float a = j < N ? row[j] * inv : 0.f;
-      if (j < Np) Lrow[j] = a;
-      if (j < NT * 16) { __nv_bfloat16 hh, ll; split_bf16(a, hh, ll); ph[j] = hh; pl[j] = ll; }
+    uint32_t* ph = reinterpret_cast<uint32_t*>(ap + warp * E3_ASTRIDE);
+    uint32_t* pl = reinterpret_cast<uint32_t*>(ap + (H + warp) * E3_ASTRIDE);
+    uint32_t* gh = reinterpret_cast<uint32_t*>(at_hi + (((long long)b * H + warp) * N + i) * Kp);
+    uint32_t* gl = reinterpret_cast<uint32_t*>(at_lo + (((long long)b * H + warp) * N + i) * Kp);
+    for (int j = 2 * lane; j < Kp; j += 64) {
+      const float a0 = j < N ? row[j] * inv : 0.f, a1 = j + 1 < N ? row[j + 1] * inv : 0.f;
+      uint32_t hh, ll;
+      split2_bf16(a0, a1, hh, ll);
+      if (j < NT * 16) { ph[j >> 1] = hh; pl[j >> 1] = ll; }
+      gh[j >> 1] = hh; gl[j >> 1] = ll;
+      if (write_L && j < Np) *reinterpret_cast<float2*>(Lrow + j) = make_float2(a0, a1);
     }
   }
   __syncthreads();
@@ -1902,12 +1909,12 @@ inline void tc_export_z(TcWorkspace& w, float* z_f32, int prec, cudaStream_t st)
 inline bool tc_ipa_edge_fused_ok(int N) { return g_tc_edge3 && N <= 256; }
 inline int tc_ipa_edge(const TcWeights& tw, TcWorkspace& w, int blk, float* L, const float* qp, const float* kp, const float* res_mask,
                        const float* Wb, const float* bb, const float* gamma, const float* WdT, const float* bd, float* feats, float* zbar, int B,
-                       int N, int Np, int prec, cudaStream_t st, long long* launches) {
+                       int N, int Np, int prec, int write_L, cudaStream_t st, long long* launches) {
   const int planes = prec == 1 ? 2 : 1;
   if (tc_ipa_edge_fused_ok(N)) {
     const size_t smem = ipa_edge3_smem(Np);
-    if (prec == 1) ipa_edge3_kernel<2><<<dim3(N, B), 256, smem, st>>>(w.z_hi, w.z_lo, L, res_mask, Wb, bb, zbar, N, Np);
-    else ipa_edge3_kernel<1><<<dim3(N, B), 256, smem, st>>>(w.z_hi, w.z_lo, L, res_mask, Wb, bb, zbar, N, Np);
+    if (prec == 1) ipa_edge3_kernel<2><<<dim3(N, B), 256, smem, st>>>(w.z_hi, w.z_lo, L, res_mask, Wb, bb, zbar, w.at_hi, w.at_lo, w.Kp, write_L, N, Np);
+    else ipa_edge3_kernel<1><<<dim3(N, B), 256, smem, st>>>(w.z_hi, w.z_lo, L, res_mask, Wb, bb, zbar, w.at_hi, w.at_lo, w.Kp, write_L, N, Np);
     if (launches) ++*launches;
     return cudaGetLastError() == cudaSuccess ? 0 : -2;
   }
@@ -1951,12 +1958,15 @@ inline int tc_ipa_logits(TcWorkspace& w, const float* proj, const float* qp, con
 inline int tc_ipa_av(TcWorkspace& w, const float* proj, const float* vp, const float* L, float* feats, float* optg, int B, int N, int Np,
                      cudaStream_t st, long long* launches) {
   const long long M = (long long)w.R * H;
-  const long long n4 = M * (w.Kp / 4);
-  split_pad_planes_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(L, Np, M, N, w.Kp, w.at_hi, w.at_lo);
-  vt_planes_kernel<<<dim3(w.Kp / 32, C_HID / 32, B * H), dim3(32, 8), 0, st>>>(proj, PROJ_ALL, PROJ_Q + C_HID, 2 * C_HID, H, C_HID, C_HID, N, w.Kp,
+  if (!tc_ipa_edge_fused_ok(N)) {     // the one-kernel edge pass has already written the probability planes
+    const long long n4 = M * (w.Kp / 4);
+    split_pad_planes_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(L, Np, M, N, w.Kp, w.at_hi, w.at_lo);
+    if (launches) ++*launches;
+  }
+  vt_planes_kernel<<<dim3(w.Kp / 64, C_HID / 32, B * H), dim3(32, 8), 0, st>>>(proj, PROJ_ALL, PROJ_Q + C_HID, 2 * C_HID, H, C_HID, C_HID, N, w.Kp,
                                                                             w.vt_hi, w.vt_lo);
-  vt_planes_kernel<<<dim3(w.Kp / 32, 2, B * H), dim3(32, 8), 0, st>>>(vp, H * PV * 3, 0, PV * 3, H, PV * 3, 64, N, w.Kp, w.vp_hi, w.vp_lo);
-  if (launches) *launches += 3;
+  vt_planes_kernel<<<dim3(w.Kp / 64, 2, B * H), dim3(32, 8), 0, st>>>(vp, H * PV * 3, 0, PV * 3, H, PV * 3, 64, N, w.Kp, w.vp_hi, w.vp_lo);
+  if (launches) *launches += 2;
   TcGemmParams p{};
   p.M = N; p.N = C_HID; p.KB0 = w.Kp / TC_BK; p.KB1 = 0; p.planes = 2; p.epi = TC_EPI_F32;
   p.m_tiles = (N + TC_BM - 1) / TC_BM; p.nch = 2;
@@ -1993,7 +2003,7 @@ inline int tc_tf_values(TcWorkspace& w, const float* qkv, const float* S, float*
   const long long M = (long long)w.R * TF_H;
   const long long n4 = M * (w.Kp / 4);
   split_pad_planes_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(S, Np, M, N, w.Kp, w.at_hi, w.at_lo);
-  vt_planes_kernel<<<dim3(w.Kp / 32, 4, B * TF_H), dim3(32, 8), 0, st>>>(qkv, 3 * TF_D, 2 * TF_D, TF_DH, TF_H, TF_DH, 128, N, w.Kp, w.vt_hi, w.vt_lo);
+  vt_planes_kernel<<<dim3(w.Kp / 64, 4, B * TF_H), dim3(32, 8), 0, st>>>(qkv, 3 * TF_D, 2 * TF_D, TF_DH, TF_H, TF_DH, 128, N, w.Kp, w.vt_hi, w.vt_lo);
   if (launches) *launches += 2;
   TcGemmParams p{};
   p.M = N; p.N = 128; p.KB0 = w.Kp / TC_BK; p.KB1 = 0; p.planes = 2; p.epi = TC_EPI_F32;

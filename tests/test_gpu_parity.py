@@ -360,6 +360,33 @@ def test_tensor_core_large_tile_counts():
     _check_forward(out, ref, f["t"].numpy(), f["rigids_t"].numpy())
 
 
+def test_tensor_core_chain_longer_than_256():
+    """N > 256 takes the two-kernel IPA edge path (pair-bias GEMM + attention kernel, K = 256 logits GEMM): bf16x3 vs fp32 engine."""
+    from gpu_common import engine
+    np.random.seed(22)
+    B, N = 1, 272
+    r7 = torch.stack([fo.sample_ref(N) for _ in range(B)])
+    f = fo.init_feats(r7)
+    f["t"] = torch.tensor([0.35], dtype=torch.float64)
+    f["sc_ca_t"] = torch.tensor(np.random.randn(B, N, 3) * 12)
+    e = engine("fp32")
+    ref = {k: v.cpu().numpy() for k, v in e.forward(f).items()}
+    e = engine("bf16x3")
+    out = e.forward(f)
+    _check_forward(out, ref, f["t"].numpy(), f["rigids_t"].numpy())
+
+
+def test_cross_check_paths_match_oracle():
+    """FD_TC_UNFUSED=1 (EdgeTransition as three GEMM launches) and FD_IPA_EDGE2=1 (two-kernel IPA edge pass) are kept as
+    independent implementations of the fused kernels: they must meet the same bars.  The switches are read at handle creation,
+    so the checks run in a child interpreter."""
+    import os, subprocess, sys
+    env = dict(os.environ, FD_TC_UNFUSED="1", FD_IPA_EDGE2="1")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-x", "-m", "gpu", "-p", "no:cacheprovider", "-k",
+                        "test_forward_golden_bf16x3 or test_forward_intermediates_bf16x3"], env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-1000:]
+
+
 # ---- reference-facing host API (se3_diffusion_b200.se3_diffuser.SE3Diffuser / score_network.ScoreNetwork) -------------------
 def _conf():
     import sys, os
