@@ -760,36 +760,42 @@ tc_edge_fused_kernel(const __grid_constant__ CUtensorMap mZh, const __grid_const
     const bool prof_on = p.prof != nullptr && blockIdx.x == 0;
     long long c_afull = 0, c_tile0 = 0; const long long c_start = clock64();
     FuRing rg{ringb, bar0, slot_bytes, (uint32_t)S, (uint32_t)p.planes, 0u, 0, prof_on};
+    // Tensor-memory layout alternates with the tile parity so that the next tile's first GEMMs never wait for the LayerNorm:
+    //   even tiles: T1 = [0,128)   (T1a | T1b), H2 = [128,512), Y = T1
+    //   odd tiles:  T1 = [384,512),             H2 = [0,384),   Y = T1
+    // An odd tile's T1 is the even tile's H2 chunks 4,5 (consumed by its G3_4/G3_5, earlier in issue order) and vice versa; only
+    // G2_0, the first write into the new H2 (which covers the previous Y), waits for the LayerNorm's read of Y.
     // G1_c: T1[c&1] = z · W1z[64c:64c+64, :]^T  (two k-blocks of z)
 #define FU_G1(c_)                                                                                                            \
   do {                                                                                                                       \
     const int x_ = (c_) & 1;                                                                                                  \
-    rg.mma_ss(zbuf(0, 0), zbuf(0, 1), tmem_base + (uint32_t)(x_ * 64), idesc64, true);                                        \
-    rg.mma_ss(zbuf(1, 0), zbuf(1, 1), tmem_base + (uint32_t)(x_ * 64), idesc64, false);                                       \
+    rg.mma_ss(zbuf(0, 0), zbuf(0, 1), t1b + (uint32_t)(x_ * 64), idesc64, true);                                              \
+    rg.mma_ss(zbuf(1, 0), zbuf(1, 1), t1b + (uint32_t)(x_ * 64), idesc64, false);                                             \
     tc_commit_elect(t1_full(x_));                                                                                             \
   } while (0)
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
-      FU_PROF(c_tile0, mbar_wait(y_empty, (it & 1u) ^ 1u));        // previous tile's Y (= T1a|T1b) copied out by the LayerNorm warps
+      const uint32_t t1b = tmem_base + ((it & 1u) ? 384u : 0u), h2b = tmem_base + ((it & 1u) ? 0u : 128u);
       FU_PROF(c_tile0, mbar_wait(z_full, it & 1u));
       tc_fence_after();
       FU_G1(0);
       FU_G1(1);
       for (int c = 0; c < 6; ++c) {
         const int x = c & 1;
+        if (c == 0) { FU_PROF(c_tile0, mbar_wait(y_empty, (it & 1u) ^ 1u)); }   // previous tile's Y (inside this tile's H2) is in registers
         FU_PROF(c_afull, mbar_wait(a_full(x), n_af[x] & 1u)); ++n_af[x];     // epilogue wrote h1_c (bf16 hi/lo) into T1[x]
         tc_fence_after();
 #pragma unroll
-        for (int n = 0; n < 3; ++n) rg.mma_ts(tmem_base + (uint32_t)(x * 64), tmem_base + 128u + (uint32_t)(n * 128), idesc128, c == 0);
+        for (int n = 0; n < 3; ++n) rg.mma_ts(t1b + (uint32_t)(x * 64), h2b + (uint32_t)(n * 128), idesc128, c == 0);
         if (c == 5) tc_commit_elect(h2_full);
         if (c + 2 < 6) FU_G1(c + 2);                               // overwrites T1[x]: ordered after G2_c by issue order
       }
-      rg.mma_ss(zbuf(0, 0), zbuf(0, 1), tmem_base, idesc128, true);     // Y = z · Wfz^T   (T1 is free: G2_4/G2_5 precede in issue order)
-      rg.mma_ss(zbuf(1, 0), zbuf(1, 1), tmem_base, idesc128, false);
+      rg.mma_ss(zbuf(0, 0), zbuf(0, 1), t1b, idesc128, true);     // Y = z · Wfz^T   (T1 is free: G2_4/G2_5 precede in issue order)
+      rg.mma_ss(zbuf(1, 0), zbuf(1, 1), t1b, idesc128, false);
       tc_commit_elect(z_empty);
       for (int c = 0; c < 6; ++c) {
         FU_PROF(c_afull, mbar_wait(a2_full(c), it & 1u));                    // epilogue wrote h2_c into H2's columns [64c, 64c+64)
         tc_fence_after();
-        rg.mma_ts(tmem_base + 128u + (uint32_t)(c * 64), tmem_base, idesc128, false);
+        rg.mma_ts(h2b + (uint32_t)(c * 64), t1b, idesc128, false);
       }
       tc_commit_elect(y_full);
     }
@@ -820,89 +826,85 @@ tc_edge_fused_kernel(const __grid_constant__ CUtensorMap mZh, const __grid_const
       }
       tmem_st_wait();
     };
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
-      const long long m = (long long)tile * TC_BM + row;
-      const bool valid0 = m < p.E;
-      const float* pP = nullptr; const float* pQ = nullptr;
-      float emask = 0.f;
+    struct RowCtx { long long m; const float* pP; const float* pQ; float emask; bool valid; };
+    auto row_ctx = [&](int tile) {
+      RowCtx rc;
+      rc.m = (long long)tile * TC_BM + row;
+      rc.pP = nullptr; rc.pQ = nullptr; rc.emask = 0.f;
+      const bool valid0 = rc.m < p.E;
       if (valid0) {
         const long long nn = (long long)p.nres * p.nres;
-        const long long b = m / nn;
-        const int rem = (int)(m - b * nn);
+        const long long b = rc.m / nn;
+        const int rem = (int)(rc.m - b * nn);
         const int ri = rem / p.nres, rj = rem - ri * p.nres;
-        pP = p.pquv + (b * p.nres + ri) * ET_NODE;          // P at +0, U at +768
-        pQ = p.pquv + (b * p.nres + rj) * ET_NODE + ET_HID;  // Q at +384 (-> +0 here), V at +896 (-> +512 here)
-        emask = p.res_mask[b * p.nres + ri] * p.res_mask[b * p.nres + rj];
+        rc.pP = p.pquv + (b * p.nres + ri) * ET_NODE;          // P at +0, U at +768
+        rc.pQ = p.pquv + (b * p.nres + rj) * ET_NODE + ET_HID;  // Q at +384 (-> +0 here), V at +896 (-> +512 here)
+        rc.emask = p.res_mask[b * p.nres + ri] * p.res_mask[b * p.nres + rj];
       }
-      const bool valid = valid0 && !p.dbg_noq;
-      // ---- epi1: h1 chunks of this group's parity.  The per-row node term Q_j (L2 latency) is requested before the wait on
-      //      the accumulator, P_i (shared by the tile's rows, L1 hits) at use. ------------------------------------------------
-      for (int c = grp; c < 6; c += 2) {
-        float v[64];
-        const int col0 = c * 64;
+      rc.valid = valid0 && !p.dbg_noq;
+      return rc;
+    };
+    // ---- epi1 step: h1 chunk c of the current tile (T1[grp] of this tile's layout).  Q_j (L2 latency) is requested before the
+    //      wait on the accumulator, P_i (shared by the tile's rows, L1 hits) at use. ----
+    auto epi1 = [&](const RowCtx& rc, uint32_t t1b, int c) {
+      const bool valid = rc.valid; const float* pP = rc.pP; const float* pQ = rc.pQ;
+      float v[64];
+      const int col0 = c * 64;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        float y8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (valid) ldg256(pQ + col0 + q * 8, y8);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[q * 8 + e] = y8[e];
+      }
+      FU_PROF(c_t1f, mbar_wait(t1_full(grp), n_t1f & 1u)); ++n_t1f;
+      tc_fence_after();
+      const uint32_t tchunk = trow + t1b + (uint32_t)(grp * 64);
+      {
+        uint32_t r0[32], r1[32];
+        tmem_ld32_nowait(tchunk, r0);
+        tmem_ld32_nowait(tchunk + 32u, r1);
+        tmem_ld_wait();
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
-          float y8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-          if (valid) ldg256(pQ + col0 + q * 8, y8);
-#pragma unroll
-          for (int e = 0; e < 8; ++e) v[q * 8 + e] = y8[e];
+          const float4 pa = valid ? __ldg(reinterpret_cast<const float4*>(pP + col0 + q * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          const float4 pb = valid ? __ldg(reinterpret_cast<const float4*>(pP + col0 + 32 + q * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          v[q * 4 + 0] = fmaxf((__uint_as_float(r0[q * 4 + 0]) + pa.x) + v[q * 4 + 0], 0.f); v[q * 4 + 1] = fmaxf((__uint_as_float(r0[q * 4 + 1]) + pa.y) + v[q * 4 + 1], 0.f);
+          v[q * 4 + 2] = fmaxf((__uint_as_float(r0[q * 4 + 2]) + pa.z) + v[q * 4 + 2], 0.f); v[q * 4 + 3] = fmaxf((__uint_as_float(r0[q * 4 + 3]) + pa.w) + v[q * 4 + 3], 0.f);
+          v[32 + q * 4 + 0] = fmaxf((__uint_as_float(r1[q * 4 + 0]) + pb.x) + v[32 + q * 4 + 0], 0.f); v[32 + q * 4 + 1] = fmaxf((__uint_as_float(r1[q * 4 + 1]) + pb.y) + v[32 + q * 4 + 1], 0.f);
+          v[32 + q * 4 + 2] = fmaxf((__uint_as_float(r1[q * 4 + 2]) + pb.z) + v[32 + q * 4 + 2], 0.f); v[32 + q * 4 + 3] = fmaxf((__uint_as_float(r1[q * 4 + 3]) + pb.w) + v[32 + q * 4 + 3], 0.f);
         }
-        FU_PROF(c_t1f, mbar_wait(t1_full(grp), n_t1f & 1u)); ++n_t1f;
-        tc_fence_after();
-        const uint32_t tchunk = trow + (uint32_t)(grp * 64);
-        {
-          uint32_t r0[32], r1[32];
-          tmem_ld32_nowait(tchunk, r0);
-          tmem_ld32_nowait(tchunk + 32u, r1);
-          tmem_ld_wait();
-#pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const float4 pa = valid ? __ldg(reinterpret_cast<const float4*>(pP + col0 + q * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
-            const float4 pb = valid ? __ldg(reinterpret_cast<const float4*>(pP + col0 + 32 + q * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
-            v[q * 4 + 0] = fmaxf((__uint_as_float(r0[q * 4 + 0]) + pa.x) + v[q * 4 + 0], 0.f); v[q * 4 + 1] = fmaxf((__uint_as_float(r0[q * 4 + 1]) + pa.y) + v[q * 4 + 1], 0.f);
-            v[q * 4 + 2] = fmaxf((__uint_as_float(r0[q * 4 + 2]) + pa.z) + v[q * 4 + 2], 0.f); v[q * 4 + 3] = fmaxf((__uint_as_float(r0[q * 4 + 3]) + pa.w) + v[q * 4 + 3], 0.f);
-            v[32 + q * 4 + 0] = fmaxf((__uint_as_float(r1[q * 4 + 0]) + pb.x) + v[32 + q * 4 + 0], 0.f); v[32 + q * 4 + 1] = fmaxf((__uint_as_float(r1[q * 4 + 1]) + pb.y) + v[32 + q * 4 + 1], 0.f);
-            v[32 + q * 4 + 2] = fmaxf((__uint_as_float(r1[q * 4 + 2]) + pb.z) + v[32 + q * 4 + 2], 0.f); v[32 + q * 4 + 3] = fmaxf((__uint_as_float(r1[q * 4 + 3]) + pb.w) + v[32 + q * 4 + 3], 0.f);
-          }
-        }
-        write_a(tchunk, v);
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(a_full(grp));
       }
-      // ---- epi2: h2 chunks of this group's parity, in place over H2 -----------------------------------------------------
-      FU_PROF(c_h2f, mbar_wait(h2_full, it & 1u));
-      tc_fence_after();
-      for (int c = grp; c < 6; c += 2) {
-        float v[64];
-        const int col0 = c * 64;
-        const uint32_t tchunk = trow + 128u + (uint32_t)(c * 64);
-        {
-          uint32_t r0[32], r1[32];
-          tmem_ld32_nowait(tchunk, r0);
-          tmem_ld32_nowait(tchunk + 32u, r1);
-          tmem_ld_wait();
-#pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const float4 ba = __ldg(reinterpret_cast<const float4*>(p.b2 + col0 + q * 4));
-            const float4 bb = __ldg(reinterpret_cast<const float4*>(p.b2 + col0 + 32 + q * 4));
-            v[q * 4 + 0] = fmaxf(__uint_as_float(r0[q * 4 + 0]) + ba.x, 0.f); v[q * 4 + 1] = fmaxf(__uint_as_float(r0[q * 4 + 1]) + ba.y, 0.f);
-            v[q * 4 + 2] = fmaxf(__uint_as_float(r0[q * 4 + 2]) + ba.z, 0.f); v[q * 4 + 3] = fmaxf(__uint_as_float(r0[q * 4 + 3]) + ba.w, 0.f);
-            v[32 + q * 4 + 0] = fmaxf(__uint_as_float(r1[q * 4 + 0]) + bb.x, 0.f); v[32 + q * 4 + 1] = fmaxf(__uint_as_float(r1[q * 4 + 1]) + bb.y, 0.f);
-            v[32 + q * 4 + 2] = fmaxf(__uint_as_float(r1[q * 4 + 2]) + bb.z, 0.f); v[32 + q * 4 + 3] = fmaxf(__uint_as_float(r1[q * 4 + 3]) + bb.w, 0.f);
-          }
-        }
-        write_a(tchunk, v);
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(a2_full(c));
-      }
+      write_a(tchunk, v);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(a_full(grp));
+    };
+    // ---- epi3 of tile lt (layout parity lt & 1): LayerNorm + mask + store.  Runs AFTER this group's first epi1 step of tile lt + 1, so
+    //      the tensor pipe already works on the next tile while these warps normalise and store. ----
+    auto epi3 = [&](const RowCtx& rc, uint32_t lt) {
+      const bool valid = rc.valid; const float* pP = rc.pP; const float* pQ = rc.pQ; const float emask = rc.emask; const long long m = rc.m;
+      const uint32_t ybase = (lt & 1u) ? 384u : 0u;
       // ---- epi3: LayerNorm + mask + store.  Warp (quad, grp) owns 64 of the row's 128 columns; the two partial (sum, sum of
-      //      squared deviations) pairs meet in smem.  Y is copied to registers and released at once so the next tile's G1 can
-      //      start; U_i + V_j are fetched before the wait. ------------------------------------------------------------------
+      //      squared deviations) pairs meet in smem.  Y goes to registers first and is released at once (the next tile's G2_0
+      //      overwrites it); U_i + V_j are added afterwards. ---------------------------------------------------------------
       {
         float v[64];
         const int cb = grp * 64;
+        FU_PROF(c_yf, mbar_wait(y_full, lt & 1u));
+        const long long c_ln0 = prof_on ? clock64() : 0;
+        tc_fence_after();
+        {
+          uint32_t r0[32], r1[32];
+          tmem_ld32_nowait(trow + ybase + (uint32_t)cb, r0);
+          tmem_ld32_nowait(trow + ybase + (uint32_t)(cb + 32), r1);
+          tmem_ld_wait();
+#pragma unroll
+          for (int q = 0; q < 32; ++q) { v[q] = __uint_as_float(r0[q]); v[32 + q] = __uint_as_float(r1[q]); }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(y_empty);
         if (valid) {
           const float* pU = pP + 2 * ET_HID + cb;
           const float* pV = pQ + (ET_HID + C_Z) + cb;   // pQ points at +384: V sits at 896 = 384 + 512
@@ -912,49 +914,35 @@ tc_edge_fused_kernel(const __grid_constant__ CUtensorMap mZh, const __grid_const
             ldg256(pU + q * 8, x8);
             ldg256(pV + q * 8, y8);
 #pragma unroll
-            for (int e = 0; e < 8; ++e) v[q * 8 + e] = x8[e] + y8[e];
+            for (int e = 0; e < 8; ++e) v[q * 8 + e] += x8[e] + y8[e];
           }
         } else {
 #pragma unroll
           for (int q = 0; q < 64; ++q) v[q] = 0.f;
         }
-        FU_PROF(c_yf, mbar_wait(y_full, it & 1u));
-        const long long c_ln0 = prof_on ? clock64() : 0;
-        tc_fence_after();
-        {
-          uint32_t r0[32], r1[32];
-          tmem_ld32_nowait(trow + (uint32_t)cb, r0);
-          tmem_ld32_nowait(trow + (uint32_t)(cb + 32), r1);
-          tmem_ld_wait();
-#pragma unroll
-          for (int q = 0; q < 32; ++q) { v[q] += __uint_as_float(r0[q]); v[32 + q] += __uint_as_float(r1[q]); }
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(y_empty);
+        // statistics: each half row gets its own (mean, M2) exactly (two local passes), then ONE exchange through smem and Chan's
+        // combination  M2 = M2_a + M2_b + 32 (mean_a - mean_b)^2  — no cancellation, half the barrier traffic of two global passes.
         float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
         for (int q = 0; q < 64; q += 4) { s0 += v[q]; s1 += v[q + 1]; s2 += v[q + 2]; s3 += v[q + 3]; }
-        const float psum = (s0 + s1) + (s2 + s3);
-        // stats buffer: [half 2][row 128][2] fp32 = 2 KB
-        const uint32_t st_mine = stats + (uint32_t)((grp * 128 + row) * 8), st_other = stats + (uint32_t)(((grp ^ 1) * 128 + row) * 8);
-        asm volatile("st.shared.f32 [%0], %1;" ::"r"(st_mine), "f"(psum) : "memory");
-        asm volatile("bar.sync %0, 64;" ::"r"(2 + quad) : "memory");     // the two warps of this quadrant
-        float osum;
-        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(osum) : "r"(st_other) : "memory");
-        const float mean = (psum + osum) * (1.f / 128.f);
+        const float mloc = ((s0 + s1) + (s2 + s3)) * (1.f / 64.f);
         float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
 #pragma unroll
         for (int q = 0; q < 64; q += 4) {
-          const float d0 = v[q] - mean, d1 = v[q + 1] - mean, d2 = v[q + 2] - mean, d3 = v[q + 3] - mean;
+          const float d0 = v[q] - mloc, d1 = v[q + 1] - mloc, d2 = v[q + 2] - mloc, d3 = v[q + 3] - mloc;
           q0 = fmaf(d0, d0, q0); q1 = fmaf(d1, d1, q1); q2 = fmaf(d2, d2, q2); q3 = fmaf(d3, d3, q3);
         }
-        const float pvar = (q0 + q1) + (q2 + q3);
-        asm volatile("st.shared.f32 [%0], %1;" ::"r"(st_mine + 4), "f"(pvar) : "memory");
-        asm volatile("bar.sync %0, 64;" ::"r"(2 + quad) : "memory");
-        float ovar;
-        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(ovar) : "r"(st_other + 4) : "memory");
-        const float rstd = rsqrtf((pvar + ovar) * (1.f / 128.f) + 1e-5f);
+        const float m2loc = (q0 + q1) + (q2 + q3);
+        // stats buffer: [half 2][row 128][2] fp32 = 2 KB
+        const uint32_t st_mine = stats + (uint32_t)((grp * 128 + row) * 8), st_other = stats + (uint32_t)(((grp ^ 1) * 128 + row) * 8);
+        asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(st_mine), "f"(mloc), "f"(m2loc) : "memory");
+        asm volatile("bar.sync %0, 64;" ::"r"(2 + quad) : "memory");     // the two warps of this quadrant
+        float omean, om2;
+        asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(omean), "=f"(om2) : "r"(st_other) : "memory");
+        asm volatile("bar.sync %0, 64;" ::"r"(2 + quad) : "memory");     // slots may be rewritten (next tile) only after both have read; cheap: the pair is aligned here
+        const float mean = 0.5f * (mloc + omean);
+        const float dm = mloc - omean;
+        const float rstd = rsqrtf(((m2loc + om2) + 32.f * dm * dm) * (1.f / 128.f) + 1e-5f);
         {
           uint32_t hw[32], lw[32];
 #pragma unroll
@@ -975,7 +963,44 @@ tc_edge_fused_kernel(const __grid_constant__ CUtensorMap mZh, const __grid_const
         }
         if (prof_on) c_ln += clock64() - c_ln0;
       }
+    };
+    RowCtx prev{};
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      const RowCtx cur = row_ctx(tile);
+      const uint32_t t1b = (it & 1u) ? 384u : 0u, h2b = (it & 1u) ? 0u : 128u;
+      epi1(cur, t1b, grp);
+      if (it > 0) epi3(prev, it - 1);
+      for (int c = grp + 2; c < 6; c += 2) epi1(cur, t1b, c);
+      // ---- epi2: h2 chunks of this group's parity, in place over H2 -----------------------------------------------------
+      FU_PROF(c_h2f, mbar_wait(h2_full, it & 1u));
+      tc_fence_after();
+      for (int c = grp; c < 6; c += 2) {
+        float v[64];
+        const int col0 = c * 64;
+        const uint32_t tchunk = trow + h2b + (uint32_t)(c * 64);
+        {
+          uint32_t r0[32], r1[32];
+          tmem_ld32_nowait(tchunk, r0);
+          tmem_ld32_nowait(tchunk + 32u, r1);
+          tmem_ld_wait();
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float4 ba = __ldg(reinterpret_cast<const float4*>(p.b2 + col0 + q * 4));
+            const float4 bb = __ldg(reinterpret_cast<const float4*>(p.b2 + col0 + 32 + q * 4));
+            v[q * 4 + 0] = fmaxf(__uint_as_float(r0[q * 4 + 0]) + ba.x, 0.f); v[q * 4 + 1] = fmaxf(__uint_as_float(r0[q * 4 + 1]) + ba.y, 0.f);
+            v[q * 4 + 2] = fmaxf(__uint_as_float(r0[q * 4 + 2]) + ba.z, 0.f); v[q * 4 + 3] = fmaxf(__uint_as_float(r0[q * 4 + 3]) + ba.w, 0.f);
+            v[32 + q * 4 + 0] = fmaxf(__uint_as_float(r1[q * 4 + 0]) + bb.x, 0.f); v[32 + q * 4 + 1] = fmaxf(__uint_as_float(r1[q * 4 + 1]) + bb.y, 0.f);
+            v[32 + q * 4 + 2] = fmaxf(__uint_as_float(r1[q * 4 + 2]) + bb.z, 0.f); v[32 + q * 4 + 3] = fmaxf(__uint_as_float(r1[q * 4 + 3]) + bb.w, 0.f);
+          }
+        }
+        write_a(tchunk, v);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(a2_full(c));
+      }
+      prev = cur;
     }
+    if (it > 0) epi3(prev, it - 1);
     if (prof_on && lane == 0) { p.prof[16] = clock64() - c_start; p.prof[17] = c_t1f; p.prof[19] = c_h2f; p.prof[20] = c_yf; p.prof[21] = c_ln; }
   }
   tc_fence_before();
