@@ -198,6 +198,17 @@ int fd_set_stage_timing(fd_handle h, int on);
 int fd_stage_times(fd_handle h, double* ms_out /* [fd_num_stages()] */, int64_t* launches_out);
 int64_t fd_forward_flops(int B, int N, int executed);   /* algorithmic FLOPs of one forward */
 
+/* ---- downstream data format: PDB text of sampled backbones ---------------------------------- */
+/* Host-only (no CUDA call): the text analysis/utils.py:39-77 write_prot_to_pdb + data/protein.py:146-219 to_pdb produce
+ * for one chain 'A', residue_index = 0..N-1: per frame `MODEL`, one ATOM line per atom with mask != 0 (atom37 order,
+ * serials from 1), `TER`, `ENDMDL`, every line padded to 80 columns + '\n'; after the last frame the 3 bytes `END`.
+ * pos [T,N,37,3] (Angstrom) float32 (pos_is_f32 != 0) or float64; mask [T,N,37] (0/1) or NULL = the reference's rule
+ * `sum(|pos|, axis=-1) > 1e-7` evaluated in pos's own precision; aatype [N] (0..20, NULL = ALA); b_factors [N,37] (NULL = 0).
+ * Writes at most cap bytes to out and the full length to *len; returns FD_EINVAL when cap is too small (len still set)
+ * or an aatype is out of range (the reference raises ValueError). */
+int fd_format_pdb(const void* pos, int pos_is_f32, const unsigned char* mask, const int* aatype, const double* b_factors, int T, int N,
+                  char* out, size_t cap, size_t* len);
+
 #ifdef __cplusplus
 }
 #endif

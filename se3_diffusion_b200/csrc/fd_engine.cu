@@ -1280,3 +1280,127 @@ extern "C" int64_t fd_forward_flops(int B, int N, int executed) {
   const double exe = ref - 3 * (688128.0 - 524288.0) * n2 - (96256.0 - 65536.0) * n2 - 4 * (8192.0 + 512.0 - 2048.0) * n2;
   return (int64_t)((executed ? exe : ref) * B);
 }
+
+// ------------------------------------------------------------------------------------------------------------------
+// PDB text of sampled backbones (host only).  Restates analysis/utils.py:39-77 (write_prot_to_pdb, create_full_prot) and
+// data/protein.py:146-219 (to_pdb) for the single-chain proteins the sampler writes; byte-exact (tests/test_pdb_writer.py).
+// ------------------------------------------------------------------------------------------------------------------
+namespace {
+const char* kAtomTypes[37] = {"N", "CA", "C", "CB", "O", "CG", "CG1", "CG2", "OG", "OG1", "SG", "CD", "CD1", "CD2", "ND1", "ND2", "OD1", "OD2", "SD",
+                              "CE", "CE1", "CE2", "CE3", "NE", "NE1", "NE2", "OE1", "OE2", "CH2", "NH1", "NH2", "OH", "CZ", "CZ2", "CZ3", "NZ", "OXT"};
+const char* kRes3[21] = {"ALA", "ARG", "ASN", "ASP", "CYS", "GLN", "GLU", "GLY", "HIS", "ILE", "LEU", "LYS", "MET", "PHE", "PRO", "SER", "THR",
+                         "TRP", "TYR", "VAL", "UNK"};
+struct PdbSink {
+  char* out; size_t cap; size_t len;
+  void line(const char* s, int n) {            // pad to 80 columns (never truncate: over-wide fields widen the line), add '\n'
+    const int pad = n < 80 ? 80 - n : 0;
+    if (len + (size_t)n + pad + 1 <= cap) {
+      memcpy(out + len, s, n);
+      memset(out + len + n, ' ', pad);
+      out[len + n + pad] = '\n';
+    }
+    len += (size_t)n + pad + 1;
+  }
+};
+// printf("%{width}.{dec}f") for dec in {2,3}, right-aligned, never truncated.  Fast path: scale, round to nearest-even, emit digits.
+// The scaled product is exact for float32-born values (24 + 10 bits), so ties resolve exactly like printf's correctly rounded
+// conversion; anything near a tie, huge or non-finite goes through snprintf itself.
+inline int fmt_fixed(char* dst, double x, int width, int dec) {
+  const double scale = dec == 3 ? 1000.0 : 100.0;
+  const double y = fabs(x) * scale;
+  if (!(y < 9.0e15)) return snprintf(dst, 64, dec == 3 ? "%*.3f" : "%*.2f", width, x);   // also NaN / inf
+  const double f = nearbyint(y);                 // round-half-even in the default rounding mode
+  const double d = fabs(y - f);
+  if (d > 0.499999 && d < 0.500001) return snprintf(dst, 64, dec == 3 ? "%*.3f" : "%*.2f", width, x);
+  unsigned long long v = (unsigned long long)f;
+  char tmp[32];
+  int n = 0;
+  for (int k = 0; k < dec; ++k) { tmp[n++] = (char)('0' + v % 10); v /= 10; }
+  tmp[n++] = '.';
+  do { tmp[n++] = (char)('0' + v % 10); v /= 10; } while (v);
+  if (std::signbit(x)) tmp[n++] = '-';
+  int w = 0;
+  for (int k = n; k < width; ++k) dst[w++] = ' ';
+  while (n) dst[w++] = tmp[--n];
+  return w;
+}
+inline int fmt_int(char* dst, long long v, int width) {     // "%{width}d", right-aligned, never truncated
+  char tmp[24];
+  int n = 0;
+  const bool neg = v < 0;
+  unsigned long long u = neg ? (unsigned long long)(-v) : (unsigned long long)v;
+  do { tmp[n++] = (char)('0' + u % 10); u /= 10; } while (u);
+  if (neg) tmp[n++] = '-';
+  int w = 0;
+  for (int k = n; k < width; ++k) dst[w++] = ' ';
+  while (n) dst[w++] = tmp[--n];
+  return w;
+}
+}  // namespace
+
+extern "C" int fd_format_pdb(const void* pos_v, int pos_is_f32, const unsigned char* mask, const int* aatype, const double* b_factors, int T,
+                             int N, char* out, size_t cap, size_t* len) {
+  if (!pos_v || !len || T < 1 || N < 1 || (!out && cap)) return fail(FD_EINVAL, "fd_format_pdb: bad arguments");
+  const float* pf = pos_is_f32 ? static_cast<const float*>(pos_v) : nullptr;
+  const double* pd = pos_is_f32 ? nullptr : static_cast<const double*>(pos_v);
+  for (int i = 0; aatype && i < N; ++i)
+    if (aatype[i] < 0 || aatype[i] > 20) return fail(FD_EINVAL, "Invalid aatypes.");
+  PdbSink sk{out, cap, 0};
+  char buf[256];
+  for (int t = 0; t < T; ++t) {
+    int n = snprintf(buf, sizeof buf, "MODEL     %d", t + 1);
+    sk.line(buf, n);
+    long long serial = 1;
+    for (int i = 0; i < N; ++i) {
+      const char* res = kRes3[aatype ? aatype[i] : 0];
+      for (int a = 0; a < 37; ++a) {
+        const size_t ia = ((size_t)t * N + i) * 37 + a;
+        double p[3];
+        bool present;
+        if (pf) {      // np.sum(np.abs(pos37), axis=-1) > 1e-7 in float32: a length-3 reduction is a plain left-to-right sum
+          const float x = pf[ia * 3], y = pf[ia * 3 + 1], z = pf[ia * 3 + 2];
+          present = ((fabsf(x) + fabsf(y)) + fabsf(z)) > 1e-7f;
+          p[0] = x; p[1] = y; p[2] = z;
+        } else {
+          p[0] = pd[ia * 3]; p[1] = pd[ia * 3 + 1]; p[2] = pd[ia * 3 + 2];
+          present = ((fabs(p[0]) + fabs(p[1])) + fabs(p[2])) > 1e-7;
+        }
+        if (mask) present = mask[ia] != 0;
+        if (!present) continue;
+        const char* nm = kAtomTypes[a];
+        char name[8];
+        if (strlen(nm) == 4) snprintf(name, sizeof name, "%s", nm); else snprintf(name, sizeof name, " %s", nm);
+        const char element[2] = {nm[0], 0};
+        // "ATOM  " serial:>5 ' ' name:<4 altloc res:>3 ' ' chain resindex:>4 icode '   ' x y z occupancy b '          ' element:>2 charge:>2
+        n = 0;
+        memcpy(buf, "ATOM  ", 6); n = 6;
+        n += fmt_int(buf + n, serial, 5);
+        buf[n++] = ' ';
+        { const int l = (int)strlen(name); memcpy(buf + n, name, l); for (int k = l; k < 4; ++k) buf[n + k] = ' '; n += l < 4 ? 4 : l; }
+        buf[n++] = ' ';
+        memcpy(buf + n, res, 3); n += 3;
+        buf[n++] = ' '; buf[n++] = 'A';
+        n += fmt_int(buf + n, i, 4);
+        buf[n++] = ' '; buf[n++] = ' '; buf[n++] = ' '; buf[n++] = ' ';
+        n += fmt_fixed(buf + n, p[0], 8, 3);
+        n += fmt_fixed(buf + n, p[1], 8, 3);
+        n += fmt_fixed(buf + n, p[2], 8, 3);
+        memcpy(buf + n, "  1.00", 6); n += 6;
+        n += fmt_fixed(buf + n, b_factors ? b_factors[(size_t)i * 37 + a] : 0.0, 6, 2);
+        memset(buf + n, ' ', 10); n += 10;
+        buf[n++] = ' '; buf[n++] = element[0];
+        buf[n++] = ' '; buf[n++] = ' ';
+        sk.line(buf, n);
+        ++serial;
+      }
+    }
+    n = snprintf(buf, sizeof buf, "%-6s%5lld      %3s %1s%4d", "TER", serial, kRes3[aatype ? aatype[N - 1] : 0], "A", N - 1);
+    sk.line(buf, n);
+    sk.line("ENDMDL", 6);
+  }
+  if (sk.len + 3 <= cap) memcpy(out + sk.len, "END", 3);
+  sk.len += 3;
+  *len = sk.len;
+  if (sk.len > cap) return fail(FD_EINVAL, "fd_format_pdb: output needs %zu bytes, capacity %zu", sk.len, cap);
+  return FD_OK;
+}
