@@ -579,7 +579,7 @@ static int forward_impl(fd_context* h, int B, int N, const float* rigids_t, cons
   if (tc) {
     if (!f.err) {
       const int rc = tc_edge_embed(h->tcw, w.tc, h->precision, w.AC, W.ee_T, W.ee_D, W.ee_w0r, seq_idx, sc_ca, res_mask, W.ee2.b, W.ee4.b,
-                                   W.ee_ln.g, W.ee_ln.b, W.blk[0].Wb, W.blk[0].bb, B, N, st, &h->launches);
+                                   W.ee_ln.g, W.ee_ln.b, B, N, st, &h->launches);
       if (rc) f.err = fail(rc == -1 ? FD_EINVAL : FD_ECUDA, "tensor-core edge embedder launch failed (%d): %s", rc, cudaGetErrorString(cudaGetLastError()));
     }
   } else {
@@ -733,8 +733,7 @@ static int forward_impl(fd_context* h, int B, int N, const float* rigids_t, cons
       f.linear(w.nb, C_Z, X.et_node, C_Z, ET_NODE, w.pquv, ET_NODE, R);
       if (tc) {
         if (!f.err) {
-          const int rc = tc_edge_transition(h->tcw, w.tc, b, h->precision, w.pquv, X.et_w2.b, X.et_ln.g, X.et_ln.b, res_mask, W.blk[b + 1].Wb,
-                                            W.blk[b + 1].bb, B, N, st, &h->launches);
+          const int rc = tc_edge_transition(h->tcw, w.tc, b, h->precision, w.pquv, X.et_w2.b, X.et_ln.g, X.et_ln.b, res_mask, B, N, st, &h->launches);
           if (rc) f.err = fail(rc == -1 ? FD_EINVAL : FD_ECUDA, "tensor-core edge transition launch failed (%d): %s", rc, cudaGetErrorString(cudaGetLastError()));
         }
       } else {

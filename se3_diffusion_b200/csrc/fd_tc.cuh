@@ -196,7 +196,6 @@ struct TcGemmParams {
   const float* residual; int ldr;
   const float* rowmask;     // [M]
   int relu;
-  const float* wb; const float* wb_bias; float* pbias;   // LN epilogue only: next IPA block's linear_b -> pair bias [M,8] (unused now)
   int lolo;                 // also accumulate a_lo·b_lo (4-term product)
   int mma_n;                // UMMA N (128, or 16 for the 8-wide pair-bias GEMM: only the first rows of the weight tile are multiplied)
   // batched mode (attention GEMMs, TC_EPI_F32 only): tile -> (batch, local tile); batch -> (outer, inner) = (bat / bat_inner, bat % bat_inner).
@@ -227,12 +226,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mA0h, const __grid_constant__
   auto tmem_full = [&](uint32_t x) { return bar0 + 8u * (2 * TC_SA + 2 * TC_SB + x); };
   auto tmem_empty = [&](uint32_t x) { return bar0 + 8u * (2 * TC_SA + 2 * TC_SB + 2 + x); };
   const uint32_t tmem_ptr_addr = bar0 + 8u * (2 * TC_SA + 2 * TC_SB + 4);
-  const uint32_t wb_smem = bar0 + 256u;           // optional linear_b image [8][128] fp32 (LN epilogue's pair bias)
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int KB = p.KB0 + p.KB1;
-  if (p.pbias)
-    for (int i = threadIdx.x; i < H * C_Z; i += TC_THREADS) asm volatile("st.shared.f32 [%0], %1;" ::"r"(wb_smem + 4u * i), "f"(p.wb[i]) : "memory");
   const int NCH = p.nch;
   const bool dbuf = NCH * TC_NC <= 256;
   const uint32_t stage_bytes = (uint32_t)p.planes * TC_PLANE_BYTES;
@@ -470,25 +466,6 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mA0h, const __grid_constant__
             *reinterpret_cast<uint4*>(p.out_hi + m * 128 + c0) = *reinterpret_cast<const uint4*>(hi);
             if (p.planes == 2) *reinterpret_cast<uint4*>(p.out_lo + m * 128 + c0) = *reinterpret_cast<const uint4*>(lo);
           }
-          if (p.pbias) {      // pair bias of the first IPA block from the freshly normalised row (fp32); linear_b staged in smem
-            float pb[H];
-#pragma unroll
-            for (int hh = 0; hh < H; ++hh) pb[hh] = __ldg(p.wb_bias + hh);
-#pragma unroll
-            for (int c = 0; c < 128; c += 4) {
-              const float4 g4 = __ldg(reinterpret_cast<const float4*>(p.ln_g + c)), b4 = __ldg(reinterpret_cast<const float4*>(p.ln_b + c));
-              const float y0 = ((v[c] - mean) * rstd * g4.x + b4.x) * emask, y1 = ((v[c + 1] - mean) * rstd * g4.y + b4.y) * emask;
-              const float y2 = ((v[c + 2] - mean) * rstd * g4.z + b4.z) * emask, y3 = ((v[c + 3] - mean) * rstd * g4.w + b4.w) * emask;
-#pragma unroll
-              for (int hh = 0; hh < H; ++hh) {
-                float w0, w1, w2, w3;
-                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(w0), "=f"(w1), "=f"(w2), "=f"(w3) : "r"(wb_smem + 4u * (uint32_t)(hh * C_Z + c)));
-                pb[hh] += (y0 * w0 + y1 * w1) + (y2 * w2 + y3 * w3);
-              }
-            }
-            *reinterpret_cast<float4*>(p.pbias + m * H) = make_float4(pb[0], pb[1], pb[2], pb[3]);
-            *reinterpret_cast<float4*>(p.pbias + m * H + 4) = make_float4(pb[4], pb[5], pb[6], pb[7]);
-          }
         }
       }
       tc_fence_before();
@@ -670,7 +647,6 @@ struct FusedParams {
   const float* pquv;        // [B*nres, 1024] = P | Q | U | V node terms
   const float* b2; const float* ln_g; const float* ln_b; const float* res_mask;
   __nv_bfloat16* out_hi; __nv_bfloat16* out_lo;
-  const float* wb; const float* wb_bias; float* pbias;   // next IPA block's linear_b [8][128], [8] -> pair bias [E,8] (fp32) emitted by the LN epilogue
   long long* prof;          // optional [32] cycle counters written by CTA 0 (developer aid)
   int dbg_noq;              // developer experiment: skip the node-term loads (results wrong; isolates their cost)
 };
@@ -1831,7 +1807,7 @@ inline int tc_launch(const CUtensorMap& a0h, const CUtensorMap& a0l, const CUten
 // Edge embedder (model/score_network.py:79-86): layer 0 = table lookup kernel -> bf16 planes; layers 2, 4 on tensor cores.
 inline int tc_edge_embed(const TcWeights& tw, TcWorkspace& w, int prec, const float* AC, const float* T, const float* D, const float* w0r,
                          const int* seq_idx, const float* sc_ca, const float* res_mask, const float* b2, const float* b4,
-                         const float* ln_g, const float* ln_b, const float* next_wb, const float* next_bb, int B, int N, cudaStream_t st,
+                         const float* ln_g, const float* ln_b, int B, int N, cudaStream_t st,
                          long long* launches) {
   const long long E = w.E;
   const int planes = prec == 1 ? 2 : 1;
@@ -1844,7 +1820,6 @@ inline int tc_edge_embed(const TcWeights& tw, TcWorkspace& w, int prec, const fl
     EmbedFusedParams f{};
     f.E = (int)E; f.planes = planes; f.nres = N; f.num_tiles = (int)((E + TC_BM - 1) / TC_BM);
     f.b2 = b2; f.b4 = b4; f.ln_g = ln_g; f.ln_b = ln_b; f.res_mask = res_mask; f.out_hi = w.z_hi; f.out_lo = w.z_lo;
-    (void)next_wb; (void)next_bb;
     const int grid = f.num_tiles < g_tc_sms ? f.num_tiles : g_tc_sms;
     tc_embed_fused_kernel<<<grid, EF_THREADS, EF_SMEM_BYTES, st>>>(w.m_e0_h, w.m_e0_l, tw.ee2.mh, tw.ee2.ml, tw.ee4.mh, tw.ee4.ml, f);
     if (launches) ++*launches;
@@ -1857,7 +1832,6 @@ inline int tc_edge_embed(const TcWeights& tw, TcWorkspace& w, int prec, const fl
   TcGemmParams q{};
   q.M = (int)E; q.N = 128; q.KB0 = 2; q.KB1 = 0; q.planes = planes; q.epi = TC_EPI_LN; q.bias = b4; q.nres = N; q.res_mask = res_mask;
   q.ln_g = ln_g; q.ln_b = ln_b; q.out_hi = w.z_hi; q.out_lo = w.z_lo;
-  (void)next_wb; (void)next_bb;   // pair bias now comes from tc_ipa_edge's own N=16 GEMM over the z planes
   if (tc_launch(w.m_e1_h, w.m_e1_l, w.m_e1_h, w.m_e1_l, tw.ee4, q, st, launches)) return -2;
   return 0;
 }
@@ -1865,7 +1839,7 @@ inline int tc_edge_embed(const TcWeights& tw, TcWorkspace& w, int prec, const fl
 // EdgeTransition (model/ipa_pytorch.py:218-233) with the separable first/last layers (node terms P,Q,U,V precomputed):
 //   h1 = relu(z·W1z^T + P_i + Q_j);  h2 = relu(h1·W2^T + b2);  z' = LN([h2|z]·[Wf|Wfz]^T + U_i + V_j)·mask
 inline int tc_edge_transition(const TcWeights& tw, TcWorkspace& w, int blk, int prec, const float* pquv, const float* b2, const float* ln_g,
-                              const float* ln_b, const float* res_mask, const float* next_wb, const float* next_bb, int B, int N,
+                              const float* ln_b, const float* res_mask, int B, int N,
                               cudaStream_t st, long long* launches) {
   const long long E = w.E;
   const int planes = prec == 1 ? 2 : 1;
@@ -1874,7 +1848,6 @@ inline int tc_edge_transition(const TcWeights& tw, TcWorkspace& w, int blk, int 
     FusedParams f{};
     f.E = (int)E; f.planes = planes; f.nres = N; f.num_tiles = (int)((E + TC_BM - 1) / TC_BM);
     f.pquv = pquv; f.b2 = b2; f.ln_g = ln_g; f.ln_b = ln_b; f.res_mask = res_mask; f.out_hi = w.z_hi; f.out_lo = w.z_lo;
-    (void)next_wb; (void)next_bb;
     f.prof = g_tc_prof;
     f.dbg_noq = getenv("FD_FU_NOQ") ? 1 : 0;
     const int grid = f.num_tiles < g_tc_sms ? f.num_tiles : g_tc_sms;
