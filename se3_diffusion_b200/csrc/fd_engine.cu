@@ -683,12 +683,17 @@ static int forward_impl(fd_context* h, int B, int N, const float* rigids_t, cons
         g.B = w.qkv + TF_D; g.ldb = 3 * TF_D; g.sB0 = (long long)N * 3 * TF_D; g.sB1 = TF_DH;
         g.C = w.S; g.ldc = Np; g.sC0 = (long long)TF_H * N * Np; g.sC1 = (long long)N * Np;
         g.M = N; g.N = N; g.K = TF_DH; g.nb0 = B; g.nb1 = TF_H; g.alpha = (float)(1.0 / sqrt((double)TF_DH));
-        if (tc) {
+        const bool one_kernel = tc && tc_tf_attn_fused_ok(N);
+        if (one_kernel) {
+          if (!f.err && tc_tf_attention(w.qkv, res_mask, w.y320, B, N, st, &h->launches))
+            f.err = fail(FD_ECUDA, "transformer attention launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+        } else if (tc) {
           if (!f.err && tc_tf_logits(w.tc, w.qkv, w.S, B, N, Np, st, &h->launches))
             f.err = fail(FD_ECUDA, "transformer logits (tensor-core) launch failed: %s", cudaGetErrorString(cudaGetLastError()));
         } else {
           f.gemm(g);
         }
+        if (!one_kernel) {
         const long long rows = (long long)B * TF_H * N;
         softmax_rows_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(w.S, Np, N, rows, (long long)TF_H * N, res_mask);
         f.check("softmax_rows");
@@ -702,6 +707,7 @@ static int forward_impl(fd_context* h, int B, int N, const float* rigids_t, cons
             f.err = fail(FD_ECUDA, "transformer values (tensor-core) launch failed: %s", cudaGetErrorString(cudaGetLastError()));
         } else {
           f.gemm(v, false);
+        }
         }
       }
       f.linear(w.y320, TF_D, T.out_proj, TF_D, TF_D, w.ff, TF_D, R, false, x, TF_D);       // x + attn

@@ -1589,12 +1589,174 @@ __global__ void __launch_bounds__(256, 3) ipa_edge3_kernel(
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Sequence-transformer self-attention, one kernel (torch.nn.TransformerEncoderLayer inside model/ipa_pytorch.py:584-593,636):
+// one CTA per (sample, head), N <= 256.  K and V of the head (dh = 80) are staged once in shared memory as bf16 hi/lo planes;
+// each of the 8 warps then runs 16-query-row tiles flash-style with mma.sync m16n8k16: S = q·k^T (3-term split product) over 64-key
+// blocks, online softmax in fp32 (keys with mask <= 0.5 excluded, a row without valid keys yields zeros — the eval-mode semantics of
+// softmax_rows_kernel), probabilities re-split to bf16 hi/lo in registers as the A operand of P·V (V through ldmatrix.trans).
+// Replaces six launches (head-padded split, logits GEMM, softmax, probability split, V transpose, values GEMM) and the [B,4,N,N]
+// round trip.  FD_TF_ATTN_GEMM=1 keeps the GEMM path (also the N > 256 path).
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t (&r)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t (&r)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x2(uint32_t addr, uint32_t& r0, uint32_t& r1) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0, %1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(addr));
+}
+
+constexpr int TFA_STRIDE = 176;     // bytes per K / V row in smem: 80 bf16 + 8 padding (ldmatrix rows land in distinct 16-byte bank groups)
+inline size_t tf_attn_smem(int N) { return (size_t)4 * ((N + 63) / 64 * 64) * TFA_STRIDE + ((N + 63) / 64 * 64) * 4; }
+
+__global__ void __launch_bounds__(256) tf_attn_kernel(const float* __restrict__ qkv, const float* __restrict__ keymask, float* __restrict__ y,
+                                                      int N, float alpha) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const int NK = (N + 63) / 64 * 64;                 // keys padded to whole 64-key blocks
+  const uint32_t kh_s = smem_u32(smem_raw), kl_s = kh_s + (uint32_t)NK * TFA_STRIDE, vh_s = kl_s + (uint32_t)NK * TFA_STRIDE,
+                 vl_s = vh_s + (uint32_t)NK * TFA_STRIDE;
+  float* kvalid = reinterpret_cast<float*>(smem_raw + (size_t)4 * NK * TFA_STRIDE);
+  const int bh = blockIdx.x, b = bh / TF_H, hh = bh - b * TF_H;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+  const float* base = qkv + (long long)b * N * (3 * TF_D) + hh * TF_DH;
+  // ---- stage K and V of this head: fp32 -> bf16 hi/lo rows ----
+  for (int idx = tid; idx < NK * (TF_DH / 4); idx += 256) {
+    const int j = idx / (TF_DH / 4), c = (idx - j * (TF_DH / 4)) * 4;
+    float4 kf = make_float4(0.f, 0.f, 0.f, 0.f), vf = kf;
+    if (j < N) {
+      kf = *reinterpret_cast<const float4*>(base + (long long)j * (3 * TF_D) + TF_D + c);
+      vf = *reinterpret_cast<const float4*>(base + (long long)j * (3 * TF_D) + 2 * TF_D + c);
+    }
+    uint32_t h0, l0, h1, l1;
+    split2_bf16(kf.x, kf.y, h0, l0); split2_bf16(kf.z, kf.w, h1, l1);
+    const uint32_t off = (uint32_t)(j * TFA_STRIDE + c * 2);
+    asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(kh_s + off), "r"(h0), "r"(h1) : "memory");
+    asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(kl_s + off), "r"(l0), "r"(l1) : "memory");
+    split2_bf16(vf.x, vf.y, h0, l0); split2_bf16(vf.z, vf.w, h1, l1);
+    asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(vh_s + off), "r"(h0), "r"(h1) : "memory");
+    asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(vl_s + off), "r"(l0), "r"(l1) : "memory");
+  }
+  for (int j = tid; j < NK; j += 256) kvalid[j] = (j < N && keymask[(long long)b * N + j] > 0.5f) ? 1.f : 0.f;
+  __syncthreads();
+  const int mi = lane >> 3, lr = lane & 7;
+  for (int mt = warp; mt * 16 < N; mt += 8) {       // 16-query-row tiles of this warp
+    const int i0 = mt * 16 + g, i1 = i0 + 8;
+    // q fragments (A operand): rows i0, i1; k-step ks covers channels 16ks + {2t, 2t+1} and {2t+8, 2t+9}
+    uint32_t qh[5][4], ql[5][4];
+#pragma unroll
+    for (int ks = 0; ks < 5; ++ks) {
+      const float2 z2 = make_float2(0.f, 0.f);
+      const float2 a0 = i0 < N ? *reinterpret_cast<const float2*>(base + (long long)i0 * (3 * TF_D) + 16 * ks + 2 * t) : z2;
+      const float2 a1 = i1 < N ? *reinterpret_cast<const float2*>(base + (long long)i1 * (3 * TF_D) + 16 * ks + 2 * t) : z2;
+      const float2 a2 = i0 < N ? *reinterpret_cast<const float2*>(base + (long long)i0 * (3 * TF_D) + 16 * ks + 2 * t + 8) : z2;
+      const float2 a3 = i1 < N ? *reinterpret_cast<const float2*>(base + (long long)i1 * (3 * TF_D) + 16 * ks + 2 * t + 8) : z2;
+      split2_bf16(a0.x, a0.y, qh[ks][0], ql[ks][0]); split2_bf16(a1.x, a1.y, qh[ks][1], ql[ks][1]);
+      split2_bf16(a2.x, a2.y, qh[ks][2], ql[ks][2]); split2_bf16(a3.x, a3.y, qh[ks][3], ql[ks][3]);
+    }
+    float o[10][4];
+#pragma unroll
+    for (int c = 0; c < 10; ++c) { o[c][0] = 0.f; o[c][1] = 0.f; o[c][2] = 0.f; o[c][3] = 0.f; }
+    float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;      // running max / partial row sums of rows i0, i1
+    for (int kb = 0; kb < NK; kb += 64) {
+      float sc[8][4];
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        sc[nt][0] = 0.f; sc[nt][1] = 0.f; sc[nt][2] = 0.f; sc[nt][3] = 0.f;
+        const uint32_t rowoff = (uint32_t)((kb + nt * 8 + lr) * TFA_STRIDE);
+#pragma unroll
+        for (int kp = 0; kp < 2; ++kp) {            // k-steps 2kp, 2kp+1: 16-byte chunks 4kp .. 4kp+3
+          uint32_t bh4[4], bl4[4];
+          ldsm_x4(kh_s + rowoff + (uint32_t)((4 * kp + mi) * 16), bh4);
+          ldsm_x4(kl_s + rowoff + (uint32_t)((4 * kp + mi) * 16), bl4);
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int ks = 2 * kp + e;
+            mma_bf16_16816(sc[nt], qh[ks][0], qh[ks][1], qh[ks][2], qh[ks][3], bh4[2 * e], bh4[2 * e + 1]);
+            mma_bf16_16816(sc[nt], qh[ks][0], qh[ks][1], qh[ks][2], qh[ks][3], bl4[2 * e], bl4[2 * e + 1]);
+            mma_bf16_16816(sc[nt], ql[ks][0], ql[ks][1], ql[ks][2], ql[ks][3], bh4[2 * e], bh4[2 * e + 1]);
+          }
+        }
+        uint32_t b0h, b1h, b0l, b1l;                 // k-step 4: chunks 8, 9
+        ldsm_x2(kh_s + rowoff + (uint32_t)((8 + (mi & 1)) * 16), b0h, b1h);
+        ldsm_x2(kl_s + rowoff + (uint32_t)((8 + (mi & 1)) * 16), b0l, b1l);
+        mma_bf16_16816(sc[nt], qh[4][0], qh[4][1], qh[4][2], qh[4][3], b0h, b1h);
+        mma_bf16_16816(sc[nt], qh[4][0], qh[4][1], qh[4][2], qh[4][3], b0l, b1l);
+        mma_bf16_16816(sc[nt], ql[4][0], ql[4][1], ql[4][2], ql[4][3], b0h, b1h);
+      }
+      // scale, mask, block maxima of the two rows
+      float bm0 = -INFINITY, bm1 = -INFINITY;
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        const float2 kv = *reinterpret_cast<const float2*>(kvalid + kb + nt * 8 + 2 * t);
+        sc[nt][0] = kv.x > 0.5f ? sc[nt][0] * alpha : -INFINITY; sc[nt][1] = kv.y > 0.5f ? sc[nt][1] * alpha : -INFINITY;
+        sc[nt][2] = kv.x > 0.5f ? sc[nt][2] * alpha : -INFINITY; sc[nt][3] = kv.y > 0.5f ? sc[nt][3] * alpha : -INFINITY;
+        bm0 = fmaxf(bm0, fmaxf(sc[nt][0], sc[nt][1])); bm1 = fmaxf(bm1, fmaxf(sc[nt][2], sc[nt][3]));
+      }
+      bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 1)); bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 2));
+      bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 1)); bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 2));
+      const float mn0 = fmaxf(m0, bm0), mn1 = fmaxf(m1, bm1);
+      const float c0 = mn0 == -INFINITY ? 1.f : expf(m0 - mn0), c1 = mn1 == -INFINITY ? 1.f : expf(m1 - mn1);   // exp(-inf) = 0 for a fresh row
+      m0 = mn0; m1 = mn1;
+      l0 *= c0; l1 *= c1;
+#pragma unroll
+      for (int c = 0; c < 10; ++c) { o[c][0] *= c0; o[c][1] *= c0; o[c][2] *= c1; o[c][3] *= c1; }
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        sc[nt][0] = mn0 == -INFINITY ? 0.f : expf(sc[nt][0] - mn0); sc[nt][1] = mn0 == -INFINITY ? 0.f : expf(sc[nt][1] - mn0);
+        sc[nt][2] = mn1 == -INFINITY ? 0.f : expf(sc[nt][2] - mn1); sc[nt][3] = mn1 == -INFINITY ? 0.f : expf(sc[nt][3] - mn1);
+        l0 += sc[nt][0] + sc[nt][1]; l1 += sc[nt][2] + sc[nt][3];
+      }
+      // O += P·V over the block's four 16-key steps
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        uint32_t ph[4], pl[4];
+        split2_bf16(sc[2 * kk][0], sc[2 * kk][1], ph[0], pl[0]); split2_bf16(sc[2 * kk][2], sc[2 * kk][3], ph[1], pl[1]);
+        split2_bf16(sc[2 * kk + 1][0], sc[2 * kk + 1][1], ph[2], pl[2]); split2_bf16(sc[2 * kk + 1][2], sc[2 * kk + 1][3], ph[3], pl[3]);
+        const uint32_t rowoff = (uint32_t)((kb + kk * 16 + (mi & 1) * 8 + lr) * TFA_STRIDE);
+#pragma unroll
+        for (int cp = 0; cp < 5; ++cp) {            // channel n-tiles 2cp, 2cp+1
+          uint32_t vh4[4], vl4[4];
+          ldsm_x4_t(vh_s + rowoff + (uint32_t)((2 * cp + (mi >> 1)) * 16), vh4);
+          ldsm_x4_t(vl_s + rowoff + (uint32_t)((2 * cp + (mi >> 1)) * 16), vl4);
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            mma_bf16_16816(o[2 * cp + e], ph[0], ph[1], ph[2], ph[3], vh4[2 * e], vh4[2 * e + 1]);
+            mma_bf16_16816(o[2 * cp + e], ph[0], ph[1], ph[2], ph[3], vl4[2 * e], vl4[2 * e + 1]);
+            mma_bf16_16816(o[2 * cp + e], pl[0], pl[1], pl[2], pl[3], vh4[2 * e], vh4[2 * e + 1]);
+          }
+        }
+      }
+    }
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+    const float inv0 = l0 > 0.f ? 1.f / l0 : 0.f, inv1 = l1 > 0.f ? 1.f / l1 : 0.f;
+    float* y0 = y + ((long long)b * N + i0) * TF_D + hh * TF_DH, *y1 = y + ((long long)b * N + i1) * TF_D + hh * TF_DH;
+#pragma unroll
+    for (int c = 0; c < 10; ++c) {
+      if (i0 < N) *reinterpret_cast<float2*>(y0 + c * 8 + 2 * t) = make_float2(o[c][0] * inv0, o[c][1] * inv0);
+      if (i1 < N) *reinterpret_cast<float2*>(y1 + c * 8 + 2 * t) = make_float2(o[c][2] * inv1, o[c][3] * inv1);
+    }
+  }
+}
+
+static int g_tc_tf_fused = 1;   // FD_TF_ATTN_GEMM=1 selects the six-launch GEMM path (cross-check; also used when N > 256)
+inline bool tc_tf_attn_fused_ok(int N) { return g_tc_tf_fused && N <= 256; }
+inline int tc_tf_attention(const float* qkv, const float* keymask, float* y, int B, int N, cudaStream_t st, long long* launches) {
+  tf_attn_kernel<<<B * TF_H, 256, tf_attn_smem(N), st>>>(qkv, keymask, y, N, (float)(1.0 / sqrt((double)TF_DH)));
+  if (launches) ++*launches;
+  return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+
 static int g_tc_edge3 = 1;   // FD_IPA_EDGE2=1 selects the two-kernel path (pair-bias GEMM + attention kernel) kept as the cross-check
 static int g_tc_fused = 1;   // FD_TC_UNFUSED=1 selects the three-launch path (kept as the fused kernel's cross-check)
 inline int tc_init(int sm_count) {
   g_tc_sms = sm_count;
   g_tc_fused = getenv("FD_TC_UNFUSED") ? 0 : 1;
   g_tc_edge3 = getenv("FD_IPA_EDGE2") ? 0 : 1;
+  g_tc_tf_fused = getenv("FD_TF_ATTN_GEMM") ? 0 : 1;
+  if (cudaFuncSetAttribute(tf_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tf_attn_smem(256)) != cudaSuccess) return -2;
   if (cudaFuncSetAttribute(ipa_edge3_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ipa_edge3_smem(256)) != cudaSuccess) return -2;
   if (cudaFuncSetAttribute(ipa_edge3_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ipa_edge3_smem(256)) != cudaSuccess) return -2;
   void* fn = nullptr;

@@ -402,11 +402,12 @@ def test_tensor_core_chain_longer_than_256():
 
 
 def test_cross_check_paths_match_oracle():
-    """FD_TC_UNFUSED=1 (EdgeTransition as three GEMM launches) and FD_IPA_EDGE2=1 (two-kernel IPA edge pass) are kept as
-    independent implementations of the fused kernels: they must meet the same bars.  The switches are read at handle creation,
+    """FD_TC_UNFUSED=1 (EdgeTransition as three GEMM launches), FD_IPA_EDGE2=1 (two-kernel IPA edge pass) and FD_TF_ATTN_GEMM=1
+    (sequence attention as batched GEMMs + softmax) are kept as independent implementations of the fused kernels: they must meet the
+    same bars.  The switches are read at handle creation,
     so the checks run in a child interpreter."""
     import os, subprocess, sys
-    env = dict(os.environ, FD_TC_UNFUSED="1", FD_IPA_EDGE2="1")
+    env = dict(os.environ, FD_TC_UNFUSED="1", FD_IPA_EDGE2="1", FD_TF_ATTN_GEMM="1")
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-x", "-m", "gpu", "-p", "no:cacheprovider", "-k",
                         "test_forward_golden_bf16x3 or test_forward_intermediates_bf16x3"], env=env, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-1000:]
