@@ -63,6 +63,38 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       "l"(map), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
+// ---- thread-block-cluster helpers (2-CTA weight multicast of the fused EdgeTransition kernel) ----
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the mbarrier at the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t rank) {
+  uint32_t ra;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(bar), "r"(rank));
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(ra) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {   // barrier with remote arrivals: cluster-scope acquire
+  uint32_t done = 0;
+  for (uint32_t spin = 0; !done; ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (!done && spin > (1u << 22)) __trap();
+  }
+}
+// TMA tile load delivered to the same smem offset (and signalling the same mbarrier offset) in every CTA of `mask`
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -587,17 +619,32 @@ struct FuRing {
   uint32_t ringb, bar0, slot_bytes, S, planes;
   uint32_t iw;
   long long c_wait; bool prof_on;
+  uint32_t cl, rank;                       // cluster mode (2-CTA weight multicast) and this CTA's rank in the pair
   __device__ __forceinline__ uint32_t slot(uint32_t s, int pl) const { return ringb + s * slot_bytes + (uint32_t)pl * TC_PLANE_BYTES; }
   __device__ __forceinline__ uint32_t full(uint32_t s) const { return bar0 + 8u * s; }
   __device__ __forceinline__ uint32_t empty(uint32_t s) const { return bar0 + 8u * (10 + s); }
-  // producer: wait for a free slot, arm it, issue the TMA loads of one weight block
+  // producer: wait for a free slot, arm it, issue the TMA loads of one weight block.
+  // Cluster mode (cl != 0): the two CTAs of a pair consume the same weight sequence, so each block is fetched from L2 ONCE and
+  // multicast into both rings.  Per slot: `empty` = this CTA's MMAs retired; `free2` (count 2) = both CTAs' slots are free (each
+  // producer arrives locally and on its peer's barrier); loads alternate between the two CTAs as issuers.
+  __device__ __forceinline__ uint32_t free2(uint32_t s) const { return bar0 + 8u * (44 + s); }
   __device__ __forceinline__ void load(const CUtensorMap* mh, const CUtensorMap* ml, int k, int n, uint32_t bytes_per_plane) {
     const uint32_t s = iw % S, ph = (iw / S) & 1u;
     if (prof_on) { const long long t0 = clock64(); mbar_wait(empty(s), ph ^ 1u); c_wait += clock64() - t0; } else mbar_wait(empty(s), ph ^ 1u);
+    if (cl) {
+      if (elect_one()) { mbar_arrive(free2(s)); mbar_arrive_remote(free2(s), rank ^ 1u); }
+      __syncwarp();
+      mbar_wait_cluster(free2(s), ph);
+    }
     if (elect_one()) {
       mbar_expect_tx(full(s), planes * bytes_per_plane);
-      tma_load_2d(slot(s, 0), mh, full(s), k, n);
-      if (planes == 2) tma_load_2d(slot(s, 1), ml, full(s), k, n);
+      if (!cl) {
+        tma_load_2d(slot(s, 0), mh, full(s), k, n);
+        if (planes == 2) tma_load_2d(slot(s, 1), ml, full(s), k, n);
+      } else if ((iw & 1u) == rank) {
+        tma_load_2d_mc(slot(s, 0), mh, full(s), k, n, (uint16_t)3);
+        if (planes == 2) tma_load_2d_mc(slot(s, 1), ml, full(s), k, n, (uint16_t)3);
+      }
     }
     __syncwarp();
     ++iw;
@@ -656,6 +703,7 @@ struct FusedParams {
     if (prof_on) { const long long _t0 = clock64(); stmt; ctr += clock64() - _t0; } else { stmt; } \
   } while (0)
 
+template <bool CL>
 __global__ void __launch_bounds__(FU_THREADS, 1)
 tc_edge_fused_kernel(const __grid_constant__ CUtensorMap mZh, const __grid_constant__ CUtensorMap mZl,
                      const __grid_constant__ CUtensorMap mW1h, const __grid_constant__ CUtensorMap mW1l,
@@ -686,6 +734,7 @@ tc_edge_fused_kernel(const __grid_constant__ CUtensorMap mZh, const __grid_const
     for (int x = 0; x < 2; ++x) { mbar_init(t1_full(x), 1); mbar_init(a_full(x), 4); }
     for (int c = 0; c < 6; ++c) mbar_init(a2_full(c), 4);
     mbar_init(h2_full, 1); mbar_init(y_full, 1); mbar_init(y_empty, 8);
+    if (CL) for (int s2 = 0; s2 < 10; ++s2) mbar_init(bar0 + 8u * (44 + s2), 2);     // free2: both CTAs of the pair released the slot
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     tma_prefetch_desc(&mZh); tma_prefetch_desc(&mW1h); tma_prefetch_desc(&mW2h); tma_prefetch_desc(&mWfh);
     if (p.planes == 2) { tma_prefetch_desc(&mZl); tma_prefetch_desc(&mW1l); tma_prefetch_desc(&mW2l); tma_prefetch_desc(&mWfl); }
@@ -696,17 +745,23 @@ tc_edge_fused_kernel(const __grid_constant__ CUtensorMap mZh, const __grid_const
   }
   tc_fence_before();
   __syncthreads();
+  if (CL) cluster_sync_all();      // the peer's barriers are initialised before any remote arrive / multicast reaches them
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_addr));
+  // Tiles of this CTA: blockIdx.x, + gridDim.x, ...  In cluster mode both CTAs of a pair run the same number of iterations (the
+  // weight sequence is shared); an iteration past the last tile computes on zero-filled TMA boxes and stores nothing.
+  const uint32_t crank = CL ? cluster_ctarank() : 0u;
+  const int first = CL ? (int)(blockIdx.x - crank) : (int)blockIdx.x;
+  const uint32_t n_it = first < p.num_tiles ? (uint32_t)((p.num_tiles - 1 - first) / (int)gridDim.x + 1) : 0u;
 
   if (warp == 0) {
     // ============================================ TMA producer ============================================
     uint32_t it = 0;
     const bool prof_on = p.prof != nullptr && blockIdx.x == 0;
     long long c_zempty = 0; const long long c_start = clock64();
-    FuRing rg{ringb, bar0, slot_bytes, (uint32_t)S, (uint32_t)p.planes, 0u, 0, prof_on};
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+    FuRing rg{ringb, bar0, slot_bytes, (uint32_t)S, (uint32_t)p.planes, 0u, 0, prof_on, CL ? 1u : 0u, crank};
+    for (int tile = blockIdx.x; it < n_it; tile += gridDim.x, ++it) {
       const int m0 = tile * TC_BM;
       FU_PROF(c_zempty, mbar_wait(z_empty, (it & 1u) ^ 1u));
       if (elect_one()) {
@@ -735,7 +790,7 @@ tc_edge_fused_kernel(const __grid_constant__ CUtensorMap mZh, const __grid_const
     uint32_t it = 0, n_af[2] = {0, 0};
     const bool prof_on = p.prof != nullptr && blockIdx.x == 0;
     long long c_afull = 0, c_tile0 = 0; const long long c_start = clock64();
-    FuRing rg{ringb, bar0, slot_bytes, (uint32_t)S, (uint32_t)p.planes, 0u, 0, prof_on};
+    FuRing rg{ringb, bar0, slot_bytes, (uint32_t)S, (uint32_t)p.planes, 0u, 0, prof_on, CL ? 1u : 0u, crank};
     // Tensor-memory layout alternates with the tile parity so that the next tile's first GEMMs never wait for the LayerNorm:
     //   even tiles: T1 = [0,128)   (T1a | T1b), H2 = [128,512), Y = T1
     //   odd tiles:  T1 = [384,512),             H2 = [0,384),   Y = T1
@@ -749,7 +804,7 @@ tc_edge_fused_kernel(const __grid_constant__ CUtensorMap mZh, const __grid_const
     rg.mma_ss(zbuf(1, 0), zbuf(1, 1), t1b + (uint32_t)(x_ * 64), idesc64, false);                                             \
     tc_commit_elect(t1_full(x_));                                                                                             \
   } while (0)
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+    for (int tile = blockIdx.x; it < n_it; tile += gridDim.x, ++it) {
       const uint32_t t1b = tmem_base + ((it & 1u) ? 384u : 0u), h2b = tmem_base + ((it & 1u) ? 0u : 128u);
       FU_PROF(c_tile0, mbar_wait(z_full, it & 1u));
       tc_fence_after();
@@ -941,7 +996,7 @@ tc_edge_fused_kernel(const __grid_constant__ CUtensorMap mZh, const __grid_const
       }
     };
     RowCtx prev{};
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+    for (int tile = blockIdx.x; it < n_it; tile += gridDim.x, ++it) {
       const RowCtx cur = row_ctx(tile);
       const uint32_t t1b = (it & 1u) ? 384u : 0u, h2b = (it & 1u) ? 0u : 128u;
       epi1(cur, t1b, grp);
@@ -981,6 +1036,7 @@ tc_edge_fused_kernel(const __grid_constant__ CUtensorMap mZh, const __grid_const
   }
   tc_fence_before();
   __syncthreads();
+  if (CL) cluster_sync_all();      // no CTA leaves while its peer may still signal its barriers
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TC_TMEM_COLS) : "memory");
@@ -1750,6 +1806,7 @@ inline int tc_tf_attention(const float* qkv, const float* keymask, float* y, int
 }
 
 static int g_tc_edge3 = 1;   // FD_IPA_EDGE2=1 selects the two-kernel path (pair-bias GEMM + attention kernel) kept as the cross-check
+static int g_tc_cluster = 0;   // FD_TC_CLUSTER=1: fused EdgeTransition as 2-CTA clusters sharing each weight block by TMA multicast
 static int g_tc_fused = 1;   // FD_TC_UNFUSED=1 selects the three-launch path (kept as the fused kernel's cross-check)
 inline int tc_init(int sm_count) {
   g_tc_sms = sm_count;
@@ -1764,7 +1821,9 @@ inline int tc_init(int sm_count) {
   if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn) return -2;
   g_encode = (PFN_encodeTiled)fn;
   if (cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES) != cudaSuccess) return -2;
-  if (cudaFuncSetAttribute(tc_edge_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FU_SMEM_BYTES) != cudaSuccess) return -2;
+  if (cudaFuncSetAttribute(tc_edge_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FU_SMEM_BYTES) != cudaSuccess) return -2;
+  if (cudaFuncSetAttribute(tc_edge_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FU_SMEM_BYTES) != cudaSuccess) return -2;
+  g_tc_cluster = getenv("FD_TC_CLUSTER") ? atoi(getenv("FD_TC_CLUSTER")) : g_tc_cluster;
   if (cudaFuncSetAttribute(tc_embed_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EF_SMEM_BYTES) != cudaSuccess) return -2;
   if (cudaFuncSetAttribute(ipa_edge2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) return -2;
   if (cudaFuncSetAttribute(ipa_edge2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) return -2;
@@ -2012,9 +2071,21 @@ inline int tc_edge_transition(const TcWeights& tw, TcWorkspace& w, int blk, int 
     f.pquv = pquv; f.b2 = b2; f.ln_g = ln_g; f.ln_b = ln_b; f.res_mask = res_mask; f.out_hi = w.z_hi; f.out_lo = w.z_lo;
     f.prof = g_tc_prof;
     f.dbg_noq = getenv("FD_FU_NOQ") ? 1 : 0;
-    const int grid = f.num_tiles < g_tc_sms ? f.num_tiles : g_tc_sms;
-    tc_edge_fused_kernel<<<grid, FU_THREADS, FU_SMEM_BYTES, st>>>(w.m_z_h, w.m_z_l, tw.w1z[blk].mh64, tw.w1z[blk].ml64, tw.w2[blk].mh,
-                                                                 tw.w2[blk].ml, tw.wf[blk].mh, tw.wf[blk].ml, f);
+    int grid = f.num_tiles < g_tc_sms ? f.num_tiles : g_tc_sms;
+    if (g_tc_cluster) {
+      grid = (grid + 1) & ~1;                 // whole pairs; a CTA without tiles still mirrors its peer's weight sequence
+      if (grid > (g_tc_sms & ~1)) grid = g_tc_sms & ~1;
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(FU_THREADS); cfg.dynamicSmemBytes = FU_SMEM_BYTES; cfg.stream = st;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      cfg.attrs = at; cfg.numAttrs = 1;
+      if (cudaLaunchKernelEx(&cfg, tc_edge_fused_kernel<true>, w.m_z_h, w.m_z_l, tw.w1z[blk].mh64, tw.w1z[blk].ml64, tw.w2[blk].mh, tw.w2[blk].ml,
+                             tw.wf[blk].mh, tw.wf[blk].ml, f) != cudaSuccess) return -2;
+    } else {
+      tc_edge_fused_kernel<false><<<grid, FU_THREADS, FU_SMEM_BYTES, st>>>(w.m_z_h, w.m_z_l, tw.w1z[blk].mh64, tw.w1z[blk].ml64, tw.w2[blk].mh,
+                                                                          tw.w2[blk].ml, tw.wf[blk].mh, tw.wf[blk].ml, f);
+    }
     if (launches) ++*launches;
     return cudaGetLastError() == cudaSuccess ? 0 : -2;
   }

@@ -411,6 +411,11 @@ def test_cross_check_paths_match_oracle():
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-x", "-m", "gpu", "-p", "no:cacheprovider", "-k",
                         "test_forward_golden_bf16x3 or test_forward_intermediates_bf16x3"], env=env, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-1000:]
+    # experimental switch: the fused EdgeTransition as 2-CTA clusters sharing every weight block through TMA multicast
+    env = dict(os.environ, FD_TC_CLUSTER="1")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-x", "-m", "gpu", "-p", "no:cacheprovider", "-k",
+                        "test_forward_golden_bf16x3 or test_tensor_core_large_tile_counts"], env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-1000:]
 
 
 # ---- reference-facing host API (se3_diffusion_b200.se3_diffuser.SE3Diffuser / score_network.ScoreNetwork) -------------------
