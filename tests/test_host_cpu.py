@@ -84,6 +84,11 @@ net = score_network.ScoreNetwork(mc, se3_diffuser.SE3Diffuser(dc))
 for name in ("paper_weights.pth", "best_weights.pth"):
     net.load_state_dict(rh.load_reference_checkpoint(name), strict=True)
 ref_net, _ = rh.build_reference(net.state_dict())
+# analysis.utils: the overlay module re-exports the reference's and swaps only the PDB writer
+from analysis import utils as au, metrics
+import se3_diffusion_b200.pdb_writer as pw
+assert "se3_diffusion_b200/overlay" in au.__file__ and metrics.__file__.startswith("/root/reference")
+assert au.write_prot_to_pdb is pw.write_prot_to_pdb and callable(au.create_full_prot) and au.CA_IDX == 1
 print("OVERLAY-OK", len(net.state_dict()))
 ''' % {"root": ROOT}
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
