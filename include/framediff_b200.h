@@ -198,6 +198,34 @@ int fd_set_stage_timing(fd_handle h, int on);
 int fd_stage_times(fd_handle h, double* ms_out /* [fd_num_stages()] */, int64_t* launches_out);
 int64_t fd_forward_flops(int B, int N, int executed);   /* algorithmic FLOPs of one forward */
 
+/* ---- training loss, forward values (first half) ------------------------------------------- */
+/* The per-sample terms of Experiment.loss_fn (experiments/train_se3_diffusion.py:538-660) from the model outputs and the
+ * noised batch: terms[b] = { rot_loss, trans_loss, bb_atom_loss, dist_mat_loss, sum } (aux_data's `batch_*` entries; the
+ * caller divides their sums by the number of non-empty samples, :662).  All pointers device memory.  Scores, scalings,
+ * rigids_0 and t are fp64 (as the reference's batch / model outputs are), frames, atoms, masks and psi fp32.
+ * The backward pass / optimizer step are not part of this library yet. */
+typedef struct {
+  const double* pred_rot_score;    /* [B,N,3]  model_out['rot_score'] */
+  const double* pred_trans_score;  /* [B,N,3] */
+  const float* pred_rigids;        /* [B,N,7] */
+  const float* pred_atom37;        /* [B,N,37,3] */
+  const double* gt_rot_score;      /* [B,N,3]  batch['rot_score'] */
+  const double* gt_trans_score;    /* [B,N,3] */
+  const double* rot_score_scaling; /* [B] */
+  const double* trans_score_scaling; /* [B] */
+  const double* rigids_0;          /* [B,N,7] */
+  const double* t;                 /* [B] */
+  const float* res_mask;           /* [B,N] */
+  const float* fixed_mask;         /* [B,N] */
+  const float* gt_psi;             /* [B,N,2] = batch['torsion_angles_sin_cos'][..., 2, :] */
+} fd_loss_in;
+typedef struct {                   /* config/base.yaml:104-115 + diffuser.diffuse_{trans,rot} */
+  double trans_loss_weight, rot_loss_weight, rot_loss_t_threshold, trans_x0_threshold, coordinate_scaling,
+      bb_atom_loss_weight, bb_atom_loss_t_filter, dist_mat_loss_weight, dist_mat_loss_t_filter, aux_loss_weight;
+  int separate_rot_loss, diffuse_trans, diffuse_rot;
+} fd_loss_cfg;
+int fd_loss_forward(fd_handle h, int B, int N, const fd_loss_in* in, const fd_loss_cfg* cfg, double* terms_dev /* [B,5] */, void* stream);
+
 /* ---- downstream data format: PDB text of sampled backbones ---------------------------------- */
 /* Host-only (no CUDA call): the text analysis/utils.py:39-77 write_prot_to_pdb + data/protein.py:146-219 to_pdb produce
  * for one chain 'A', residue_index = 0..N-1: per frame `MODEL`, one ATOM line per atom with mask != 0 (atom37 order,

@@ -779,3 +779,76 @@ def inference_loop(w, feats, num_t=500, min_t=0.01, center=True, aux_traj=False,
         ret["psi_pred"] = psi_pred[None]
         ret["rigid_0_traj"] = flip(all_bb0)
     return ret
+
+
+# --------------------------------------------------------------------------------------------------------------
+# DSM training loss, forward values (Experiment.loss_fn, experiments/train_se3_diffusion.py:524-693) — the terms computed from the
+# model outputs and the noised batch (the model call and the self-conditioning coin flip stay with the caller).
+# --------------------------------------------------------------------------------------------------------------
+DEFAULT_EXP_CONF = dict(trans_loss_weight=1.0, rot_loss_weight=0.5, rot_loss_t_threshold=0.2, separate_rot_loss=True,
+                        trans_x0_threshold=1.0, coordinate_scaling=0.1, bb_atom_loss_weight=1.0, bb_atom_loss_t_filter=0.25,
+                        dist_mat_loss_weight=1.0, dist_mat_loss_t_filter=0.25, aux_loss_weight=0.25)   # config/base.yaml:104-115
+
+
+def loss_terms(model_out, batch, exp_conf=None, diffuse_trans=True, diffuse_rot=True):
+    """Per-sample loss terms [B] and the normalised scalars of loss_fn (train_se3_diffusion.py:538-680)."""
+    c = dict(DEFAULT_EXP_CONF, **(exp_conf or {}))
+    T = lambda x: torch.as_tensor(x)
+    bb_mask = T(batch["res_mask"])
+    diffuse_mask = 1 - T(batch["fixed_mask"])
+    loss_mask = bb_mask * diffuse_mask
+    B, N = bb_mask.shape
+    t = T(batch["t"])
+    gt_rot, gt_trans = T(batch["rot_score"]), T(batch["trans_score"])
+    rot_sc, trans_sc = T(batch["rot_score_scaling"]), T(batch["trans_score_scaling"])
+    batch_loss_mask = torch.any(bb_mask.bool(), dim=-1)
+    pred_rot = T(model_out["rot_score"]) * diffuse_mask[..., None]
+    pred_trans = T(model_out["trans_score"]) * diffuse_mask[..., None]
+    denom = loss_mask.sum(dim=-1) + 1e-10
+    # translation: score loss above the threshold, x0 loss below (:553-573)
+    trans_score_loss = torch.sum((gt_trans - pred_trans) ** 2 * loss_mask[..., None] / trans_sc[:, None, None] ** 2, dim=(-1, -2)) / denom
+    gt_x0 = T(batch["rigids_0"])[..., 4:] * c["coordinate_scaling"]
+    pred_x0 = T(model_out["rigids"])[..., 4:] * c["coordinate_scaling"]
+    trans_x0_loss = torch.sum((gt_x0 - pred_x0) ** 2 * loss_mask[..., None], dim=(-1, -2)) / denom
+    trans_loss = trans_score_loss * (t > c["trans_x0_threshold"]) + trans_x0_loss * (t <= c["trans_x0_threshold"])
+    trans_loss = trans_loss * c["trans_loss_weight"] * int(diffuse_trans)
+    # rotation (:576-607)
+    if c["separate_rot_loss"]:
+        gt_angle = torch.norm(gt_rot, dim=-1, keepdim=True)
+        gt_axis = gt_rot / (gt_angle + 1e-6)
+        pr_angle = torch.norm(pred_rot, dim=-1, keepdim=True)
+        pr_axis = pred_rot / (pr_angle + 1e-6)
+        axis_loss = torch.sum((gt_axis - pr_axis) ** 2 * loss_mask[..., None], dim=(-1, -2)) / denom
+        angle_loss = torch.sum((gt_angle - pr_angle) ** 2 * loss_mask[..., None] / rot_sc[:, None, None] ** 2, dim=(-1, -2)) / denom
+        angle_loss = angle_loss * c["rot_loss_weight"] * (t > c["rot_loss_t_threshold"])
+        rot_loss = angle_loss + axis_loss
+    else:
+        rot_loss = torch.sum((gt_rot - pred_rot) ** 2 * loss_mask[..., None] / rot_sc[:, None, None] ** 2, dim=(-1, -2)) / denom
+        rot_loss = rot_loss * c["rot_loss_weight"] * (t > c["rot_loss_t_threshold"])
+    rot_loss = rot_loss * int(diffuse_rot)
+    # backbone atoms (:611-630): ground truth through compute_backbone of rigids_0 (fp32) and the psi torsion (index 2)
+    pred_a = T(model_out["atom37"])[:, :, :5]
+    r0 = T(batch["rigids_0"]).to(F32)
+    gt_psi = T(batch["torsion_angles_sin_cos"])[..., 2, :]
+    gt_a37, gt_m37, _ = compute_backbone(quat_to_rotmat(r0[..., :4]), r0[..., 4:], gt_psi)
+    gt_a, a_mask = gt_a37[:, :, :5], gt_m37[:, :, :5]
+    bb_m = a_mask * loss_mask[..., None]
+    bb_atom_loss = torch.sum((pred_a - gt_a) ** 2 * bb_m[..., None], dim=(-1, -2, -3)) / (bb_m.sum(dim=(-1, -2)) + 1e-10)
+    bb_atom_loss = bb_atom_loss * c["bb_atom_loss_weight"] * (t < c["bb_atom_loss_t_filter"]) * c["aux_loss_weight"]
+    # pairwise distances of the 5N backbone atoms, pairs closer than 6 A in the ground truth (:633-660)
+    gt_f, pr_f = gt_a.reshape(B, N * 5, 3), pred_a.reshape(B, N * 5, 3)
+    gt_d = torch.linalg.norm(gt_f[:, :, None, :] - gt_f[:, None, :, :], dim=-1)
+    pr_d = torch.linalg.norm(pr_f[:, :, None, :] - pr_f[:, None, :, :], dim=-1)
+    flat_loss = torch.tile(loss_mask[:, :, None], (1, 1, 5)).reshape(B, N * 5)
+    flat_res = torch.tile(bb_mask[:, :, None], (1, 1, 5)).reshape(B, N * 5)
+    gt_d = gt_d * flat_loss[..., None]
+    pr_d = pr_d * flat_loss[..., None]
+    pair_mask = flat_loss[..., None] * flat_res[:, None, :]
+    pair_mask = pair_mask * (gt_d < 6)
+    dist_mat_loss = torch.sum((gt_d - pr_d) ** 2 * pair_mask, dim=(1, 2)) / (torch.sum(pair_mask, dim=(1, 2)) - N)
+    dist_mat_loss = dist_mat_loss * c["dist_mat_loss_weight"] * (t < c["dist_mat_loss_t_filter"]) * c["aux_loss_weight"]
+    final = rot_loss + trans_loss + bb_atom_loss + dist_mat_loss
+    norm = lambda x: x.sum() / (batch_loss_mask.sum() + 1e-10)
+    return {"batch_train_loss": final, "batch_rot_loss": rot_loss, "batch_trans_loss": trans_loss, "batch_bb_atom_loss": bb_atom_loss,
+            "batch_dist_mat_loss": dist_mat_loss, "total_loss": norm(final), "rot_loss": norm(rot_loss), "trans_loss": norm(trans_loss),
+            "bb_atom_loss": norm(bb_atom_loss), "dist_mat_loss": norm(dist_mat_loss)}

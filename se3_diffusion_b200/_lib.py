@@ -13,6 +13,18 @@ class ForwardIn(C.Structure):
                 ("fixed_mask", c_voidp), ("seq_idx", c_voidp), ("sc_ca_t", c_voidp), ("gt_psi", c_voidp)]
 
 
+class LossIn(C.Structure):
+    _fields_ = [(k, c_voidp) for k in ("pred_rot_score", "pred_trans_score", "pred_rigids", "pred_atom37", "gt_rot_score", "gt_trans_score",
+                                       "rot_score_scaling", "trans_score_scaling", "rigids_0", "t", "res_mask", "fixed_mask", "gt_psi")]
+
+
+class LossCfg(C.Structure):
+    _fields_ = [(k, C.c_double) for k in ("trans_loss_weight", "rot_loss_weight", "rot_loss_t_threshold", "trans_x0_threshold",
+                                          "coordinate_scaling", "bb_atom_loss_weight", "bb_atom_loss_t_filter", "dist_mat_loss_weight",
+                                          "dist_mat_loss_t_filter", "aux_loss_weight")] + \
+               [(k, C.c_int) for k in ("separate_rot_loss", "diffuse_trans", "diffuse_rot")]
+
+
 class ForwardOut(C.Structure):
     _fields_ = [("rot_score", c_voidp), ("trans_score", c_voidp), ("psi", c_voidp), ("rigids", c_voidp),
                 ("atom37", c_voidp), ("atom14", c_voidp)]
@@ -68,6 +80,7 @@ SYMBOLS = {
     "fd_set_stage_timing": (C.c_int, [c_voidp, C.c_int]),
     "fd_stage_times": (C.c_int, [c_voidp, c_f64p, C.POINTER(C.c_int64)]),
     "fd_forward_flops": (C.c_int64, [C.c_int, C.c_int, C.c_int]),
+    "fd_loss_forward": (C.c_int, [c_voidp, C.c_int, C.c_int, c_voidp, c_voidp, c_voidp, c_voidp]),
     "fd_format_pdb": (C.c_int, [c_voidp, C.c_int, C.POINTER(C.c_ubyte), C.POINTER(C.c_int), c_f64p, C.c_int, C.c_int, C.c_void_p, C.c_size_t,
                                 C.POINTER(C.c_size_t)]),
 }

@@ -1287,6 +1287,34 @@ extern "C" int64_t fd_forward_flops(int B, int N, int executed) {
 }
 
 // ------------------------------------------------------------------------------------------------------------------
+// DSM loss, forward values (include/framediff_b200.h: fd_loss_forward)
+// ------------------------------------------------------------------------------------------------------------------
+extern "C" int fd_loss_forward(fd_handle h, int B, int N, const fd_loss_in* in, const fd_loss_cfg* cfg, double* terms_dev, void* stream) {
+  if (!h || !in || !cfg || !terms_dev || B < 1 || N < 1) return fail(FD_EINVAL, "fd_loss_forward: bad arguments");
+  if (!in->pred_rot_score || !in->pred_trans_score || !in->pred_rigids || !in->pred_atom37 || !in->gt_rot_score || !in->gt_trans_score ||
+      !in->rot_score_scaling || !in->trans_score_scaling || !in->rigids_0 || !in->t || !in->res_mask || !in->fixed_mask || !in->gt_psi)
+    return fail(FD_EINVAL, "fd_loss_forward: null input pointer");
+  const size_t smem = (size_t)30 * N * sizeof(float);
+  if (smem > 200 * 1024) return fail(FD_EINVAL, "fd_loss_forward: N = %d too long (pair-distance tile needs %zu bytes of shared memory)", N, smem);
+  CK(cudaSetDevice(h->device));
+  static bool attr_set = false;
+  if (!attr_set) { CK(cudaFuncSetAttribute(loss_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr_set = true; }
+  LossArgs a{};
+  a.pred_rot = in->pred_rot_score; a.pred_trans = in->pred_trans_score; a.pred_rigids = in->pred_rigids; a.pred_atom37 = in->pred_atom37;
+  a.gt_rot = in->gt_rot_score; a.gt_trans = in->gt_trans_score; a.rot_scaling = in->rot_score_scaling; a.trans_scaling = in->trans_score_scaling;
+  a.rigids_0 = in->rigids_0; a.t = in->t; a.res_mask = in->res_mask; a.fixed_mask = in->fixed_mask; a.gt_psi = in->gt_psi;
+  a.trans_loss_weight = cfg->trans_loss_weight; a.rot_loss_weight = cfg->rot_loss_weight; a.rot_loss_t_threshold = cfg->rot_loss_t_threshold;
+  a.trans_x0_threshold = cfg->trans_x0_threshold; a.coordinate_scaling = cfg->coordinate_scaling; a.bb_atom_loss_weight = cfg->bb_atom_loss_weight;
+  a.bb_atom_loss_t_filter = cfg->bb_atom_loss_t_filter; a.dist_mat_loss_weight = cfg->dist_mat_loss_weight;
+  a.dist_mat_loss_t_filter = cfg->dist_mat_loss_t_filter; a.aux_loss_weight = cfg->aux_loss_weight;
+  a.separate_rot_loss = cfg->separate_rot_loss; a.diffuse_trans = cfg->diffuse_trans; a.diffuse_rot = cfg->diffuse_rot;
+  a.terms = terms_dev; a.N = N;
+  loss_forward_kernel<<<B, 256, smem, static_cast<cudaStream_t>(stream)>>>(a);
+  CK(cudaGetLastError());
+  return FD_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
 // PDB text of sampled backbones (host only).  Restates analysis/utils.py:39-77 (write_prot_to_pdb, create_full_prot) and
 // data/protein.py:146-219 (to_pdb) for the single-chain proteins the sampler writes; byte-exact (tests/test_pdb_writer.py).
 // ------------------------------------------------------------------------------------------------------------------

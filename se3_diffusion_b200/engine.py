@@ -327,3 +327,50 @@ def _inference_fn(self, data_init: dict, num_t: int = 500, min_t: float = 0.01, 
 FrameDiffEngine.forward_marginal = _forward_marginal
 FrameDiffEngine.score_scaling = _score_scaling
 FrameDiffEngine.inference_fn = _inference_fn
+
+
+# ---- training loss, forward values (Experiment.loss_fn, experiments/train_se3_diffusion.py:524-693) -------------------------------
+DEFAULT_EXP_CONF = dict(trans_loss_weight=1.0, rot_loss_weight=0.5, rot_loss_t_threshold=0.2, separate_rot_loss=True, trans_x0_threshold=1.0,
+                        coordinate_scaling=0.1, bb_atom_loss_weight=1.0, bb_atom_loss_t_filter=0.25, dist_mat_loss_weight=1.0,
+                        dist_mat_loss_t_filter=0.25, aux_loss_weight=0.25)   # config/base.yaml:104-115
+
+
+def loss_forward(engine: "FrameDiffEngine", model_out: dict, batch: dict, exp_conf: Optional[dict] = None, diffuse_trans: bool = True,
+                 diffuse_rot: bool = True) -> dict:
+    """The loss values of the reference's loss_fn for given model outputs and noised batch, computed on the device by
+    fd_loss_forward: returns aux_data's entries (`batch_*` per sample, the normalised scalars, `examples_per_step`, `res_length`) as
+    torch tensors on the engine's device.  No autograd graph: the backward pass is not part of this library yet."""
+    from ._lib import LossCfg, LossIn
+    dev = torch.device("cuda", engine.device)
+    conf = dict(DEFAULT_EXP_CONF, **({} if exp_conf is None else dict(exp_conf)))
+
+    def dv(x, dtype):
+        return torch.as_tensor(x).to(device=dev, dtype=dtype).contiguous()
+
+    res_mask = dv(batch["res_mask"], torch.float32)
+    B, N = res_mask.shape
+    keep = dict(
+        pred_rot_score=dv(model_out["rot_score"], torch.float64), pred_trans_score=dv(model_out["trans_score"], torch.float64),
+        pred_rigids=dv(model_out["rigids"], torch.float32), pred_atom37=dv(model_out["atom37"], torch.float32),
+        gt_rot_score=dv(batch["rot_score"], torch.float64), gt_trans_score=dv(batch["trans_score"], torch.float64),
+        rot_score_scaling=dv(batch["rot_score_scaling"], torch.float64), trans_score_scaling=dv(batch["trans_score_scaling"], torch.float64),
+        rigids_0=dv(batch["rigids_0"], torch.float64), t=dv(batch["t"], torch.float64), res_mask=res_mask,
+        fixed_mask=dv(batch["fixed_mask"], torch.float32), gt_psi=dv(torch.as_tensor(batch["torsion_angles_sin_cos"])[..., 2, :], torch.float32))
+    assert keep["pred_atom37"].shape == (B, N, 37, 3) and keep["rigids_0"].shape == (B, N, 7)
+    lin = LossIn(*[_ptr(keep[k]) for k, _ in LossIn._fields_])
+    cfg = LossCfg(*[float(conf[k]) for k, ty in LossCfg._fields_ if ty is C.c_double], int(bool(conf["separate_rot_loss"])),
+                  int(bool(diffuse_trans)), int(bool(diffuse_rot)))
+    terms = torch.empty((B, 5), dtype=torch.float64, device=dev)
+    check(engine.lib.fd_loss_forward(engine._h, B, N, C.byref(lin), C.byref(cfg), _ptr(terms), None))
+    n_valid = torch.any(res_mask > 0, dim=-1).sum() + 1e-10
+    out = {"batch_rot_loss": terms[:, 0], "batch_trans_loss": terms[:, 1], "batch_bb_atom_loss": terms[:, 2],
+           "batch_dist_mat_loss": terms[:, 3], "batch_train_loss": terms[:, 4]}
+    for k in ("rot", "trans", "bb_atom", "dist_mat"):
+        out[f"{k}_loss"] = out[f"batch_{k}_loss"].sum() / n_valid
+    out["total_loss"] = out["batch_train_loss"].sum() / n_valid
+    out["examples_per_step"] = torch.tensor(B)
+    out["res_length"] = torch.mean(torch.sum(res_mask.double(), dim=-1))
+    return out
+
+
+FrameDiffEngine.loss_forward = loss_forward

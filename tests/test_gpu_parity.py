@@ -506,3 +506,21 @@ def test_inference_fn_numpy_noise_matches_reference_golden(eng):
     assert tuple(out["psi_pred"].shape) == tuple(g["psi_pred"].shape)
     assert_close(out["prot_traj"][-1], g["prot_traj"][-1], 0, norm_rel=TOL, name="step-1 atom37")
     assert_close(out["rigid_traj"][-2][..., 4:], g["rigid_traj"][-2][..., 4:], 0, norm_rel=TOL, name="step-1 trans")
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_loss_forward_vs_reference_loss_fn(eng, tag):
+    """SURVEY row a27 (forward half): fd_loss_forward on the reference's own batch and model outputs vs the values its real
+    Experiment.loss_fn produced (golden), every term per sample; and end to end from our forward of the same batch."""
+    g = golden(f"loss_{tag}")
+    batch = {k[3:]: v for k, v in g.items() if k.startswith("in_")}
+    mo = {k[4:]: v for k, v in g.items() if k.startswith("out_")}
+    got = eng.loss_forward(mo, batch)
+    for k in ("batch_rot_loss", "batch_trans_loss", "batch_bb_atom_loss", "batch_dist_mat_loss", "batch_train_loss", "total_loss", "rot_loss",
+              "trans_loss", "bb_atom_loss", "dist_mat_loss"):
+        assert_close(got[k].cpu().numpy(), g["aux_" + k], 2e-6, atol=1e-9, name=k)
+    # the same loss from OUR forward of the batch (fp32 engine): model parity (1e-4) carries through to the loss
+    f = {k: torch.as_tensor(batch[k]) for k in ("rigids_t", "res_mask", "fixed_mask", "seq_idx", "t", "sc_ca_t", "torsion_angles_sin_cos")}
+    ours = eng.forward(f)
+    got2 = eng.loss_forward(ours, batch)
+    assert_close(got2["batch_train_loss"].cpu().numpy(), g["aux_batch_train_loss"], 5e-4, name="loss from our forward")
