@@ -341,7 +341,7 @@ def loss_forward(engine: "FrameDiffEngine", model_out: dict, batch: dict, exp_co
     fd_loss_forward: returns aux_data's entries (`batch_*` per sample, the normalised scalars, `examples_per_step`, `res_length`) as
     torch tensors on the engine's device.  No autograd graph: the backward pass is not part of this library yet."""
     from ._lib import LossCfg, LossIn
-    dev = torch.device("cuda", engine.device)
+    dev = engine.device if isinstance(engine.device, torch.device) else torch.device("cuda", int(engine.device))
     conf = dict(DEFAULT_EXP_CONF, **({} if exp_conf is None else dict(exp_conf)))
 
     def dv(x, dtype):
