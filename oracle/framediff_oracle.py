@@ -491,13 +491,19 @@ def ipa(w, pre, s, z, quat, trans, mask, trace=None):
     return _linear(feats, w, pre + "linear_out")
 
 
-def seq_transformer(w, pre, x, mask):
+def seq_transformer(w, pre, x, mask, float_mask_quirk=False):
     """nn.TransformerEncoder(2 × post-norm ReLU layers, d=320, 4 heads, ff=320), eval/no-grad semantics:
-    padded keys are excluded and padded query rows come back as exact zeros."""
+    padded keys are excluded and padded query rows come back as exact zeros.
+    float_mask_quirk=True restates what torch does whenever autograd is recording (any training step, and loss_fn().backward() even
+    on an eval-mode module): the fused fast path is off and the FLOAT `src_key_padding_mask = 1 - mask` the reference passes
+    (model/ipa_pytorch.py:636) is ADDED to the attention logits — padded keys stay in the softmax with a +1 bias, nothing is zeroed."""
     B, N, D = x.shape
     H = TFMR_HEADS
     dh = D // H
-    key_bias = torch.where(mask > 0.5, 0.0, float("-inf")).to(x.dtype)[:, None, None, :]
+    if float_mask_quirk:
+        key_bias = (1.0 - mask).to(x.dtype)[:, None, None, :]
+    else:
+        key_bias = torch.where(mask > 0.5, 0.0, float("-inf")).to(x.dtype)[:, None, None, :]
     for l in range(TFMR_LAYERS):
         p = f"{pre}layers.{l}."
         qkv = torch.nn.functional.linear(x, w[p + "self_attn.in_proj_weight"], w[p + "self_attn.in_proj_bias"])
@@ -511,7 +517,7 @@ def seq_transformer(w, pre, x, mask):
         x = _layer_norm(x + _linear(y, w, p + "self_attn.out_proj"), w, p + "norm1")
         ff = _linear(torch.relu(_linear(x, w, p + "linear1")), w, p + "linear2")
         x = _layer_norm(x + ff, w, p + "norm2")
-    return x * mask[..., None]
+    return x if float_mask_quirk else x * mask[..., None]
 
 
 def edge_transition(w, pre, node, edge):
@@ -527,7 +533,7 @@ def edge_transition(w, pre, node, edge):
     return _layer_norm(y, w, pre + "layer_norm").reshape(B, N, N, C_Z)
 
 
-def score_network_forward(w, feats, use_cached_score=False, trace: Optional[dict] = None):
+def score_network_forward(w, feats, use_cached_score=False, trace: Optional[dict] = None, float_mask_quirk=False):
     """ScoreNetwork.forward (model/score_network.py:170-215) + IpaScore.forward (model/ipa_pytorch.py:611-672).
 
     feats: res_mask, fixed_mask, seq_idx, t, sc_ca_t, rigids_t, torsion_angles_sin_cos (tensors, batch first).
@@ -556,7 +562,7 @@ def score_network_forward(w, feats, use_cached_score=False, trace: Optional[dict
         upd = ipa(w, T + f"ipa_{b}.", node, edge, quat, trans, bb_mask, trace=tr) * bb_mask[..., None]
         node = _layer_norm(node + upd, w, T + f"ipa_ln_{b}")
         x = torch.cat([node, _linear(node0, w, T + f"skip_embed_{b}")], dim=-1)
-        x = seq_transformer(w, T + f"seq_tfmr_{b}.", x, bb_mask)
+        x = seq_transformer(w, T + f"seq_tfmr_{b}.", x, bb_mask, float_mask_quirk=float_mask_quirk)
         node = node + _linear(x, w, T + f"post_tfmr_{b}")
         p = T + f"node_transition_{b}."
         h = torch.relu(_linear(node, w, p + "linear_1"))

@@ -74,6 +74,18 @@ def main():
         save.update({"out_" + k: v.detach().numpy() for k, v in mo.items() if torch.is_tensor(v)})
         save.update({"aux_" + k: np.asarray(v.detach().numpy() if torch.is_tensor(v) else v) for k, v in aux.items()})
         save["loss"] = np.asarray(loss.detach().numpy())
+        # gradients of the normalised loss w.r.t. every parameter (eval-mode module, the semantics this repo implements; same coin flip):
+        # the backward KAT for the next round's kernels — all 282 gradient norms and three full gradients
+        random.seed(rnd)
+        net.zero_grad(set_to_none=True)
+        loss_g, _ = ex.loss_fn(dict(batch))
+        loss_g.backward()
+        names = [n for n, _ in net.named_parameters()]
+        save["grad_names"] = np.array(names)
+        save["grad_norms"] = np.array([-1.0 if p_.grad is None else float(p_.grad.double().norm()) for _, p_ in net.named_parameters()])
+        for n_ in ("score_model.trunk.ipa_0.linear_b.weight", "score_model.trunk.edge_transition_0.final_layer.weight",
+                   "embedding_layer.edge_embedder.0.bias"):
+            save["grad::" + n_] = dict(net.named_parameters())[n_].grad.numpy()
         np.savez_compressed(os.path.join(HERE, f"loss_{tag}.npz"), **save)
         print(tag, float(loss), {k: float(np.asarray(v).sum()) for k, v in aux.items() if k.startswith("batch_")})
 
