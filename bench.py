@@ -130,8 +130,8 @@ def cpu_baseline(nres, num_t, cpu_steps, state):
 
 
 def synthetic_state():
-    from oracle import framediff_oracle as fo      # weights only (deterministic random init of the architecture)
-    return fo.synthetic_weights(0)
+    from se3_diffusion_b200.synthetic import synthetic_weights      # deterministic random init of the architecture
+    return synthetic_weights(0)
 
 
 def run_reference(args):
@@ -245,11 +245,9 @@ def main():
     # ---- roofline of the dominant kernel: EdgeTransition (87 % of the reference's FLOPs) ----------------------------------
     roof = None
     if rank == 0:
-        from oracle import framediff_oracle as fo
+        from se3_diffusion_b200.synthetic import init_feats, random_frames
         pk = peaks()
-        np.random.seed(0)
-        r7 = torch.stack([fo.sample_ref(N) for _ in range(min(B, 4))]).repeat((B + 3) // 4, 1, 1)[:B]
-        f = fo.init_feats(r7); f["t"] = torch.full((B,), 0.5)
+        f = init_feats(random_frames(B, N, seed=0), t=0.5)
         eng.forward(f, want_atoms=False); torch.cuda.synchronize(dev)
         eng.stage_timing(True)
         reps = 3

@@ -140,3 +140,33 @@ def test_sharded_sampling_host_logic_gloo_world2(tmp_path):
     outs = [p.communicate(timeout=300)[0] for p in procs]
     for r, (p, o) in enumerate(zip(procs, outs)):
         assert p.returncode == 0 and f"RANK-OK {r}" in o, o
+
+
+def test_package_synthetic_weights_equal_the_oracles():
+    """bench.py / tools generate weights with se3_diffusion_b200.synthetic (product side, never imports oracle/); they are the very
+    arrays the parity tests use from the oracle (same schema order, same MT19937 stream)."""
+    from oracle import framediff_oracle as fo
+    from se3_diffusion_b200 import synthetic
+    a, b = synthetic.synthetic_weights(0), fo.synthetic_weights(0)
+    assert list(a) == list(b) and len(a) == 282
+    assert all(np.array_equal(a[k], b[k]) for k in a)
+    f = synthetic.init_feats(synthetic.random_frames(2, 16, seed=1))
+    assert f["rigids_t"].shape == (2, 16, 7) and torch.allclose(f["rigids_t"][..., :4].norm(dim=-1), torch.ones(2, 16), atol=1e-6)
+
+
+def test_product_code_never_imports_the_oracle():
+    """Only tests/, __graft_entry__.smoke() and bench.py's CPU-baseline / reference legs may touch oracle/."""
+    import re
+    offenders = []
+    for root in ("se3_diffusion_b200", "tools"):
+        for dp, _, fns in os.walk(os.path.join(ROOT, root)):
+            for fn in fns:
+                if fn.endswith(".py") and re.search(r"^\s*(from|import)\s+oracle\b", open(os.path.join(dp, fn)).read(), re.M):
+                    offenders.append(os.path.join(dp, fn))
+    assert not offenders, offenders
+    src = open(os.path.join(ROOT, "bench.py")).read()
+    legs = [m.start() for m in re.finditer(r"^\s*from oracle import", src, re.M)]
+    allowed = [src.index("def cpu_baseline"), src.index("def run_reference")] if "def cpu_baseline" in src else []
+    for pos in legs:        # every oracle import sits inside the CPU-baseline or the reference-arm function
+        fn_start = max(m.start() for m in re.finditer(r"^def \w+", src[:pos], re.M))
+        assert src[fn_start:fn_start + 40].startswith(("def cpu_baseline", "def run_reference")), src[fn_start:fn_start + 60]

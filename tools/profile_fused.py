@@ -8,7 +8,7 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from oracle import framediff_oracle as fo  # noqa: E402
+from se3_diffusion_b200 import synthetic as fo
 from se3_diffusion_b200 import FrameDiffEngine  # noqa: E402
 
 prec = sys.argv[1] if len(sys.argv) > 1 else "bf16x3"
@@ -17,7 +17,7 @@ N = int(sys.argv[3]) if len(sys.argv) > 3 else 256
 eng = FrameDiffEngine(0, prec)
 eng.load_weights(fo.synthetic_weights(0))
 np.random.seed(0)
-r7 = torch.stack([fo.sample_ref(N) for _ in range(min(B, 4))]).repeat((B + 3) // 4, 1, 1)[:B]
+r7 = fo.random_frames(B, N, seed=0)
 f = fo.init_feats(r7)
 f["t"] = torch.full((B,), 0.5)
 eng.forward(f, want_atoms=False)
