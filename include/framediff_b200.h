@@ -198,6 +198,10 @@ int fd_set_stage_timing(fd_handle h, int on);
 int fd_stage_times(fd_handle h, double* ms_out /* [fd_num_stages()] */, int64_t* launches_out);
 int64_t fd_forward_flops(int B, int N, int executed);   /* algorithmic FLOPs of one forward */
 
+/* Developer aid: role-level cycle counters of the fused EdgeTransition kernel (CTA 0; tools/profile_fused.py).  on != 0 arms the
+ * counters for the following forwards; out32 (host, 32 x int64, may be NULL) receives the last values. */
+int fd_debug_tc_profile(fd_handle h, int on, long long* out32);
+
 /* ---- training loss, forward values (first half) ------------------------------------------- */
 /* The per-sample terms of Experiment.loss_fn (experiments/train_se3_diffusion.py:538-660) from the model outputs and the
  * noised batch: terms[b] = { rot_loss, trans_loss, bb_atom_loss, dist_mat_loss, sum } (aux_data's `batch_*` entries; the

@@ -80,6 +80,7 @@ SYMBOLS = {
     "fd_set_stage_timing": (C.c_int, [c_voidp, C.c_int]),
     "fd_stage_times": (C.c_int, [c_voidp, c_f64p, C.POINTER(C.c_int64)]),
     "fd_forward_flops": (C.c_int64, [C.c_int, C.c_int, C.c_int]),
+    "fd_debug_tc_profile": (C.c_int, [c_voidp, C.c_int, C.POINTER(C.c_longlong)]),
     "fd_loss_forward": (C.c_int, [c_voidp, C.c_int, C.c_int, c_voidp, c_voidp, c_voidp, c_voidp]),
     "fd_format_pdb": (C.c_int, [c_voidp, C.c_int, C.POINTER(C.c_ubyte), C.POINTER(C.c_int), c_f64p, C.c_int, C.c_int, C.c_void_p, C.c_size_t,
                                 C.POINTER(C.c_size_t)]),

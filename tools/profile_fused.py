@@ -22,7 +22,6 @@ f = fo.init_feats(r7)
 f["t"] = torch.full((B,), 0.5)
 eng.forward(f, want_atoms=False)
 lib = eng.lib
-lib.fd_debug_tc_profile.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
 buf = (C.c_longlong * 32)()
 lib.fd_debug_tc_profile(eng._h, 1, None)
 eng.forward(f, want_atoms=False)
