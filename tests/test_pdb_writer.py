@@ -75,3 +75,33 @@ def test_overlay_module_next_to_reference(tmp_path):
     a = ref_au.write_prot_to_pdb(pos, str(tmp_path / "ref.pdb"), no_indexing=True)
     b = mod.write_prot_to_pdb(pos, str(tmp_path / "ours.pdb"), no_indexing=True)
     assert open(a, "rb").read() == open(b, "rb").read()
+
+
+def test_fixed_point_formatter_equals_printf_on_hard_values():
+    """fd_format_pdb's own %8.3f / %6.2f (scale, round-half-even, emit digits; snprintf near ties and beyond 9e15) against Python's
+    correctly rounded formatting: float32-born values (exact ties possible), float64 values adjacent to decimal ties, zeros of both
+    signs, values that round up into a new digit, huge and tiny magnitudes."""
+    rng = np.random.RandomState(3)
+    vals = [0.0, -0.0, 0.0005, -0.0005, 0.0015, 0.0025, 999.9995, -999.9995, 9999.9995, 99999.9996, 1e-12, -1e-12, 123456789.125, 1e15,
+            0.5 ** 11, 3 * 0.5 ** 11, -5 * 0.5 ** 12, 0.125, 0.375, 2.0625]
+    vals += list(rng.randn(3000) * 37.0)
+    vals += [float(np.float32(v)) for v in rng.randn(3000) * 37.0]
+    ties = (rng.randint(-10 ** 6, 10 ** 6, 2000) + 0.5) / 1000.0          # decimal ties: the nearest doubles lie just above or below
+    vals += list(ties) + [float(np.nextafter(t, np.inf)) for t in ties[:500]] + [float(np.nextafter(t, -np.inf)) for t in ties[:500]]
+    vals = np.array(vals, dtype=np.float64)
+    n = len(vals) // 3 * 3
+    pos = np.zeros((1, n // 3, 37, 3))
+    pos[0, :, 1, :] = vals[:n].reshape(-1, 3)                               # CA slot
+    pos[0, :, 0, 0] = 1.0                                                   # keep residues present even if a CA row is all-zero
+    bf = np.zeros((n // 3, 37)); bf[:, 1] = np.abs(vals[:n:3]) % 1000.0
+    txt = pdb_writer.format_pdb(pos, b_factors=bf).decode().split("\n")
+    ca = [l for l in txt if l.startswith("ATOM") and l[12:16] == " CA "]
+    k = 0
+    for i in range(n // 3):
+        x, y, z = vals[3 * i:3 * i + 3]
+        if abs(x) + abs(y) + abs(z) <= 1e-7:
+            continue
+        want = f"{x:>8.3f}{y:>8.3f}{z:>8.3f}{1.0:>6.2f}{bf[i, 1]:>6.2f}"
+        assert ca[k][30:30 + len(want)] == want, (i, x, y, z, ca[k])
+        k += 1
+    assert k == len(ca)
