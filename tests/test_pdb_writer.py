@@ -75,6 +75,18 @@ def test_overlay_module_next_to_reference(tmp_path):
     a = ref_au.write_prot_to_pdb(pos, str(tmp_path / "ref.pdb"), no_indexing=True)
     b = mod.write_prot_to_pdb(pos, str(tmp_path / "ours.pdb"), no_indexing=True)
     assert open(a, "rb").read() == open(b, "rb").read()
+    # the way Sampler.save_traj calls it (experiments/inference_se3_diffusion.py:272-287): suffix-less paths, indexed names,
+    # b-factors 100 on diffused residues
+    bfac = np.tile((np.arange(30) % 3 > 0).astype(float)[:, None] * 100, (1, 37))
+    for sub, w in (("r", ref_au.write_prot_to_pdb), ("o", mod.write_prot_to_pdb)):
+        d = tmp_path / sub
+        d.mkdir()
+        p1 = w(pos[0], str(d / "sample"), b_factors=bfac)
+        p2 = w(pos, str(d / "bb_traj"), b_factors=bfac)
+        p3 = w(pos[0], str(d / "sample"), b_factors=bfac)
+        assert [os.path.basename(x) for x in (p1, p2, p3)] == ["sample_1.pdb", "bb_traj_1.pdb", "sample_2.pdb"]
+    for fn in ("sample_1.pdb", "bb_traj_1.pdb", "sample_2.pdb"):
+        assert open(tmp_path / "r" / fn, "rb").read() == open(tmp_path / "o" / fn, "rb").read()
 
 
 def test_fixed_point_formatter_equals_printf_on_hard_values():
