@@ -168,6 +168,8 @@ typedef struct {
   const float* res_mask;    /* [B,N] or NULL (= ones) */
   const float* fixed_mask;  /* [B,N] or NULL (= zeros) */
   const int32_t* seq_idx;   /* [B,N] or NULL (= 1..N) */
+  const float* gt_psi;      /* [B,N,2] = torsion_angles_sin_cos[..., 2, :] or NULL (= zeros): the psi imputed on fixed (motif)
+                               residues, model/score_network.py:196-199 */
 } fd_sample_in;
 
 typedef struct {

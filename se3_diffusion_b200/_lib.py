@@ -38,7 +38,7 @@ class SampleCfg(C.Structure):
 
 class SampleIn(C.Structure):
     _fields_ = [("z_axis", c_voidp), ("u_angle", c_voidp), ("z_trans0", c_voidp), ("z_rot", c_voidp), ("z_trans", c_voidp),
-                ("rigids_init", c_voidp), ("res_mask", c_voidp), ("fixed_mask", c_voidp), ("seq_idx", c_voidp)]
+                ("rigids_init", c_voidp), ("res_mask", c_voidp), ("fixed_mask", c_voidp), ("seq_idx", c_voidp), ("gt_psi", c_voidp)]
 
 
 class SampleOut(C.Structure):

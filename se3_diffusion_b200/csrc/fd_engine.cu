@@ -41,6 +41,13 @@ static int fail(int code, const char* fmt, ...) {
     if (_r != FD_OK) return _r; \
   } while (0)
 
+// Restores the caller's current device when an entry point returns (the handle's device is only current inside the call).
+struct DevGuard {
+  int prev = -1, dev;
+  explicit DevGuard(int d) : dev(d) { if (cudaGetDevice(&prev) != cudaSuccess) prev = -1; if (prev != d) cudaSetDevice(d); }
+  ~DevGuard() { if (prev >= 0 && prev != dev) cudaSetDevice(prev); }
+};
+
 extern "C" const char* fd_last_error(void) { return g_err; }
 extern "C" const char* fd_version(void) { return "framediff_b200 0.1 (sm_100a)"; }
 
@@ -68,7 +75,8 @@ struct Workspace {
 struct LoopBufs {   // device state of fd_sample_*
   int B = 0, N = 0, num_t = 0, aux = 0;
   char* base = nullptr; size_t bytes = 0;
-  float *rigids, *sc_ca, *res_mask, *fixed_mask, *psi, *rigids_pred, *atom37, *atom37_0, *rigids_snap;
+  float *rigids, *sc_ca, *res_mask, *fixed_mask, *psi, *rigids_pred, *atom37, *atom37_0, *rigids_snap, *gt_psi;
+  bool have_gt_psi = false;
   int* seq_idx;
   double *rot_score, *trans_score, *cur_t, *cur_sigma, *z_rot, *z_trans, *z_axis, *u_angle, *z_trans0;
   StepSched* sched; double* sched_sigma; int* step;
@@ -100,7 +108,21 @@ struct fd_context {
   long long stage_launches[ST_COUNT];
   long long launches = 0;            // kernels launched since last reset
   int sm_count = 148;
+  // one captured denoise step, kept across fd_sample_* calls while every pointer / by-value argument baked into it is unchanged
+  struct GraphCache {
+    cudaGraph_t graph = nullptr; cudaGraphExec_t exec = nullptr; long long per_step = 0;
+    int B = 0, N = 0, num_t = 0, aux = 0, inject = 0, center = 0, precision = -1, have_psi = 0;
+    double noise_scale = 0; uint64_t seed = 0; long long first_sample = 0;
+    const void *ws_base = nullptr, *lb_base = nullptr, *warena = nullptr;
+  } gc;
+  cudaEvent_t ev_fwd = nullptr;      // recorded after fd_forward on the caller's stream; the sampling stream waits on it (shared workspace)
+  bool fwd_pending = false;
 };
+static void free_graph(fd_context* h) {
+  if (h->gc.exec) cudaGraphExecDestroy(h->gc.exec);
+  if (h->gc.graph) cudaGraphDestroy(h->gc.graph);
+  h->gc = fd_context::GraphCache();
+}
 
 struct Launcher {  // counts launches, optional per-stage timing
   fd_context* h; cudaStream_t st;
@@ -171,6 +193,7 @@ extern "C" int fd_create(fd_handle* out, int device) {
   h->device = device;
   h->sm_count = prop.multiProcessorCount;
   CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  CK(cudaEventCreateWithFlags(&h->ev_fwd, cudaEventDisableTiming));
   memset(h->stage_ms, 0, sizeof(h->stage_ms));
   memset(h->stage_launches, 0, sizeof(h->stage_launches));
   // constants
@@ -212,18 +235,21 @@ extern "C" int fd_create(fd_handle* out, int device) {
 }
 
 static void free_ws(fd_context* h) {
+  free_graph(h);
   if (h->ws.base) cudaFree(h->ws.base);
   h->ws = Workspace();
 }
 static void free_lb(fd_context* h) {
+  free_graph(h);
   if (h->lb.base) cudaFree(h->lb.base);
   h->lb = LoopBufs();
 }
 
 extern "C" int fd_destroy(fd_handle h) {
   if (!h) return FD_OK;
-  cudaSetDevice(h->device);
+  DevGuard dev_guard(h->device);
   cudaStreamSynchronize(h->stream);
+  free_graph(h);
   free_ws(h); free_lb(h);
   for (auto& kv : h->dbg) cudaFree(kv.second.first);
   for (auto& kv : h->igso3_rows) cudaFree(kv.second.first);
@@ -231,6 +257,7 @@ extern "C" int fd_destroy(fd_handle h) {
   tc_free_weights(h->tcw);
   cudaFree(h->d_sigma_grid); cudaFree(h->d_cdf_t1); cudaFree(h->d_omega); cudaFree(h->d_sched1);
   if (h->d_t_tmp) cudaFree(h->d_t_tmp);
+  if (h->ev_fwd) cudaEventDestroy(h->ev_fwd);
   cudaStreamDestroy(h->stream);
   delete h;
   return FD_OK;
@@ -282,7 +309,7 @@ struct Packer {   // builds one host image, records offsets, then fixes up devic
 
 extern "C" int fd_load_weights(fd_handle h, const float* const* P) {
   if (!h || !P) return fail(FD_EINVAL, "fd_load_weights: null argument");
-  CK(cudaSetDevice(h->device));
+  DevGuard dev_guard(h->device);
   const auto& schema = param_schema();
   std::map<std::string, const float*> M;
   for (size_t i = 0; i < schema.size(); ++i) {
@@ -403,6 +430,7 @@ extern "C" int fd_load_weights(fd_handle h, const float* const* P) {
   lin(W.tor1, tp + "linear_1", C_S, C_S); lin(W.tor2, tp + "linear_2", C_S, C_S); lin(W.torf, tp + "linear_final", 2, C_S);
 
   cudaStreamSynchronize(h->stream);
+  free_graph(h);
   if (h->warena) { cudaFree(h->warena); h->warena = nullptr; }
   h->warena_bytes = pk.host.size() * sizeof(float);
   CK(cudaMalloc(&h->warena, h->warena_bytes));
@@ -799,10 +827,12 @@ extern "C" int fd_forward(fd_handle h, int B, int N, const fd_forward_in* in, co
     return fail(FD_EINVAL, "fd_forward: a required input pointer is NULL");
   if (!out->rot_score || !out->trans_score || !out->psi || !out->rigids) return fail(FD_EINVAL, "fd_forward: a required output pointer is NULL");
   if (out->rigids == in->rigids_t) return fail(FD_EINVAL, "fd_forward: out->rigids must not alias in->rigids_t");
-  CK(cudaSetDevice(h->device));
+  DevGuard dev_guard(h->device);
   cudaStream_t st = (cudaStream_t)stream;
-  return forward_impl(h, B, N, in->rigids_t, in->t, in->t_is_f32, in->sigma, in->res_mask, in->fixed_mask, in->seq_idx, in->sc_ca_t,
-                      in->gt_psi, out, nullptr, st);
+  const int rc = forward_impl(h, B, N, in->rigids_t, in->t, in->t_is_f32, in->sigma, in->res_mask, in->fixed_mask, in->seq_idx, in->sc_ca_t,
+                              in->gt_psi, out, nullptr, st);
+  if (rc == FD_OK && st != h->stream) { CK(cudaEventRecord(h->ev_fwd, st)); h->fwd_pending = true; }
+  return rc;
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -810,7 +840,7 @@ extern "C" int fd_forward(fd_handle h, int B, int N, const fd_forward_in* in, co
 // ------------------------------------------------------------------------------------------------------------------
 extern "C" int fd_igso3_score(fd_handle h, int64_t n, const float* vec, const double* sigma, double* score_out, void* stream) {
   if (!h || !vec || !sigma || !score_out || n <= 0) return fail(FD_EINVAL, "fd_igso3_score: bad argument");
-  CK(cudaSetDevice(h->device));
+  DevGuard dev_guard(h->device);
   cudaStream_t st = (cudaStream_t)stream;
   igso3_score_kernel<<<(unsigned)((n + 7) / 8), 256, 0, st>>>(vec, sigma, score_out, n);
   CK(cudaGetLastError());
@@ -844,7 +874,7 @@ static int build_igso3_rows(fd_context* h, int nrows, const int* idx, double* pd
 extern "C" int fd_igso3_tables_host(fd_handle h, int nrows, const int32_t* sigma_idx, double* pdf, double* cdf, double* score_norms,
                                     double* score_scaling) {
   if (!h || nrows <= 0 || !sigma_idx) return fail(FD_EINVAL, "fd_igso3_tables_host: bad argument");
-  CK(cudaSetDevice(h->device));
+  DevGuard dev_guard(h->device);
   return build_igso3_rows(h, nrows, sigma_idx, pdf, cdf, score_norms, score_scaling);
 }
 
@@ -853,7 +883,7 @@ extern "C" int fd_sample_ref(fd_handle h, int64_t n, const double* z_axis, const
   if (!h || n <= 0 || !rigids_out) return fail(FD_EINVAL, "fd_sample_ref: bad argument");
   if ((z_axis || u_angle || z_trans) && !(z_axis && u_angle && z_trans)) return fail(FD_EINVAL, "fd_sample_ref: inject all three noise arrays or none");
   if (!z_axis && residues_per_sample <= 0) return fail(FD_EINVAL, "fd_sample_ref: residues_per_sample must be > 0");
-  CK(cudaSetDevice(h->device));
+  DevGuard dev_guard(h->device);
   cudaStream_t st = (cudaStream_t)stream;
   sample_ref_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(z_axis, u_angle, z_trans, seed, first_sample, residues_per_sample,
                                                                  h->d_cdf_t1, h->d_omega, rigids_out, n);
@@ -876,7 +906,7 @@ extern "C" int fd_reverse_step(fd_handle h, int B, int N, float* rigids_io, cons
   if (!h || !rigids_io || !rot_score || !trans_score || B <= 0 || N <= 0) return fail(FD_EINVAL, "fd_reverse_step: bad argument");
   if (!(t >= 0.0 && t <= 1.0)) return fail(FD_EINVAL, "Invalid t=%g", t);   // so3_diffuser.py:194 / r3_diffuser.py:27
   if ((z_rot == nullptr) != (z_trans == nullptr)) return fail(FD_EINVAL, "fd_reverse_step: inject both noise arrays or none");
-  CK(cudaSetDevice(h->device));
+  DevGuard dev_guard(h->device);
   cudaStream_t st = (cudaStream_t)stream;
   StepSched sc{t, so3_g_host(t), r3_b_host(t), dt};
   CK(cudaMemcpyAsync(h->d_sched1, &sc, sizeof(sc), cudaMemcpyHostToDevice, st));
@@ -896,7 +926,7 @@ extern "C" int fd_forward_marginal(fd_handle h, int64_t n, const float* rigids_0
   if (!h || n <= 0 || !rigids_0 || !z_axis || !u_angle || !z_trans || !rigids_t || !rot_score || !trans_score)
     return fail(FD_EINVAL, "fd_forward_marginal: bad argument");
   if (!(t >= 0.0 && t <= 1.0)) return fail(FD_EINVAL, "Invalid t=%g", t);
-  CK(cudaSetDevice(h->device));
+  DevGuard dev_guard(h->device);
   cudaStream_t st = (cudaStream_t)stream;
   const int idx = sigma_idx_host(h->h_sigma_grid, t);
   // cdf row + score scaling for this sigma index: built on the GPU once and cached
@@ -925,7 +955,7 @@ extern "C" int fd_forward_marginal(fd_handle h, int64_t n, const float* rigids_0
 extern "C" int fd_score_scaling(fd_handle h, double t, double* rot_scaling, double* trans_scaling) {
   if (!h) return fail(FD_EINVAL, "null handle");
   if (!(t >= 0.0 && t <= 1.0)) return fail(FD_EINVAL, "Invalid t=%g", t);
-  CK(cudaSetDevice(h->device));
+  DevGuard dev_guard(h->device);
   const int idx = sigma_idx_host(h->h_sigma_grid, t);
   auto it = h->igso3_rows.find(idx);
   if (it == h->igso3_rows.end()) {
@@ -947,7 +977,7 @@ extern "C" int fd_score_scaling(fd_handle h, double t, double* rot_scaling, doub
 
 extern "C" int fd_compute_backbone(fd_handle h, int64_t n, const float* rigids, const float* psi, float* atom37, float* atom14, void* stream) {
   if (!h || n <= 0 || !rigids || !psi) return fail(FD_EINVAL, "fd_compute_backbone: bad argument");
-  CK(cudaSetDevice(h->device));
+  DevGuard dev_guard(h->device);
   cudaStream_t st = (cudaStream_t)stream;
   compute_backbone_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(rigids, psi, atom37, atom14, n);
   CK(cudaGetLastError());
@@ -1012,7 +1042,7 @@ static int ensure_lb(fd_context* h, int B, int N, int num_t, int aux, bool injec
   std::vector<Item> items = {
       {(void**)&L.rigids, R * 7 * 4}, {(void**)&L.sc_ca, R * 3 * 4}, {(void**)&L.res_mask, R * 4}, {(void**)&L.fixed_mask, R * 4},
       {(void**)&L.psi, R * 2 * 4}, {(void**)&L.rigids_pred, R * 7 * 4}, {(void**)&L.atom37, R * 111 * 4}, {(void**)&L.atom37_0, R * 111 * 4},
-      {(void**)&L.rigids_snap, R * 7 * 4}, {(void**)&L.seq_idx, R * 4}, {(void**)&L.rot_score, R * 3 * 8}, {(void**)&L.trans_score, R * 3 * 8},
+      {(void**)&L.rigids_snap, R * 7 * 4}, {(void**)&L.gt_psi, R * 2 * 4}, {(void**)&L.seq_idx, R * 4}, {(void**)&L.rot_score, R * 3 * 8}, {(void**)&L.trans_score, R * 3 * 8},
       {(void**)&L.cur_t, (size_t)B * 8}, {(void**)&L.cur_sigma, (size_t)B * 8},
       {(void**)&L.z_rot, inject ? (size_t)(num_t > 1 ? num_t - 1 : 1) * R * 3 * 8 : 0},
       {(void**)&L.z_trans, inject ? (size_t)(num_t > 1 ? num_t - 1 : 1) * R * 3 * 8 : 0},
@@ -1049,6 +1079,7 @@ static int run_loop(fd_context* h, const fd_sample_cfg* cfg, bool inject_steps, 
     // the network sees t rounded to fp32 (t * ones(fp32)); sigma is quantised from that value (du.move_to_np(t))
     ssig[s] = h->h_sigma_grid[sigma_idx_host(h->h_sigma_grid, (double)(float)t)];
   }
+  if (h->fwd_pending) { CK(cudaStreamWaitEvent(st, h->ev_fwd, 0)); h->fwd_pending = false; }
   CK(cudaMemcpyAsync(L.sched, sched.data(), num_t * sizeof(StepSched), cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(L.sched_sigma, ssig.data(), num_t * sizeof(double), cudaMemcpyHostToDevice, st));
   CK(cudaMemsetAsync(L.step, 0, sizeof(int), st));
@@ -1058,8 +1089,8 @@ static int run_loop(fd_context* h, const fd_sample_cfg* cfg, bool inject_steps, 
 
   fd_forward_out fo{L.rot_score, L.trans_score, L.psi, L.rigids_pred, L.atom37_0, nullptr};
   auto forward = [&](bool write_sc) -> int {
-    return forward_impl(h, B, N, L.rigids, L.cur_t, 1, L.cur_sigma, L.res_mask, L.fixed_mask, L.seq_idx, L.sc_ca, nullptr, &fo,
-                        write_sc ? L.sc_ca : nullptr, st);
+    return forward_impl(h, B, N, L.rigids, L.cur_t, 1, L.cur_sigma, L.res_mask, L.fixed_mask, L.seq_idx, L.sc_ca,
+                        L.have_gt_psi ? L.gt_psi : nullptr, &fo, write_sc ? L.sc_ca : nullptr, st);
   };
   auto step_body = [&]() -> int {
     set_step_kernel<<<(B + 127) / 128, 128, 0, st>>>(L.sched, L.sched_sigma, L.step, L.cur_t, L.cur_sigma, B);
@@ -1102,23 +1133,33 @@ static int run_loop(fd_context* h, const fd_sample_cfg* cfg, bool inject_steps, 
   }
   const int nrev = num_t - 1;   // steps with t > min_t
   long long per_step = 0;
-  if (cfg->use_graph && nrev > 0) {
-    h->stage_timing = false; h->debug = false;
-    cudaGraph_t graph = nullptr; cudaGraphExec_t exec = nullptr;
-    const long long l0 = h->launches;
-    CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-    int rc = step_body();
-    cudaError_t ce = cudaStreamEndCapture(st, &graph);
-    h->stage_timing = saved_timing; h->debug = saved_debug;
-    if (rc != FD_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
-    if (ce != cudaSuccess) return fail(FD_ECUDA, "graph capture failed: %s", cudaGetErrorString(ce));
-    per_step = h->launches - l0;
-    h->launches = l0;
-    CK(cudaGraphInstantiate(&exec, graph, 0));
-    for (int s = 0; s < nrev; ++s) CK(cudaGraphLaunch(exec, st));
+  if (cfg->use_graph && nrev > 0 && !saved_timing && !saved_debug) {
+    fd_context::GraphCache& G = h->gc;
+    const bool hit = G.exec && G.B == B && G.N == N && G.num_t == num_t && G.aux == cfg->aux_traj && G.inject == (int)inject_steps &&
+                     G.center == cfg->center && G.precision == h->precision && G.have_psi == (int)L.have_gt_psi &&
+                     G.noise_scale == cfg->noise_scale && G.seed == cfg->seed && G.first_sample == cfg->first_sample &&
+                     G.ws_base == h->ws.base && G.lb_base == L.base && G.warena == h->warena;
+    if (!hit) {
+      free_graph(h);
+      h->stage_timing = false; h->debug = false;
+      const long long l0 = h->launches;
+      CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+      int rc = step_body();
+      cudaError_t ce = cudaStreamEndCapture(st, &G.graph);
+      h->stage_timing = saved_timing; h->debug = saved_debug;
+      if (rc != FD_OK) { free_graph(h); return rc; }
+      if (ce != cudaSuccess) { free_graph(h); return fail(FD_ECUDA, "graph capture failed: %s", cudaGetErrorString(ce)); }
+      G.per_step = h->launches - l0;
+      h->launches = l0;
+      CK(cudaGraphInstantiate(&G.exec, G.graph, 0));
+      G.B = B; G.N = N; G.num_t = num_t; G.aux = cfg->aux_traj; G.inject = inject_steps; G.center = cfg->center; G.precision = h->precision;
+      G.have_psi = L.have_gt_psi; G.noise_scale = cfg->noise_scale; G.seed = cfg->seed; G.first_sample = cfg->first_sample;
+      G.ws_base = h->ws.base; G.lb_base = L.base; G.warena = h->warena;
+    }
+    per_step = G.per_step;
+    for (int s = 0; s < nrev; ++s) CK(cudaGraphLaunch(G.exec, st));
     h->launches += per_step * nrev;
     CK(cudaStreamSynchronize(st));
-    cudaGraphExecDestroy(exec); cudaGraphDestroy(graph);
   } else {
     for (int s = 0; s < nrev; ++s) CKI(step_body());
   }
@@ -1133,7 +1174,8 @@ static int run_loop(fd_context* h, const fd_sample_cfg* cfg, bool inject_steps, 
     // rigids_t is both input and output here: the head kernel reads rigids_t rows it then overwrites (same warp, after
     // all its reads), so run the forward into rigids_pred and copy.
     fd_forward_out ftmp{L.rot_score, L.trans_score, L.psi, L.rigids_pred, L.atom37, nullptr};
-    CKI(forward_impl(h, B, N, L.rigids, L.cur_t, 1, L.cur_sigma, L.res_mask, L.fixed_mask, L.seq_idx, L.sc_ca, nullptr, &ftmp, nullptr, st));
+    CKI(forward_impl(h, B, N, L.rigids, L.cur_t, 1, L.cur_sigma, L.res_mask, L.fixed_mask, L.seq_idx, L.sc_ca,
+                     L.have_gt_psi ? L.gt_psi : nullptr, &ftmp, nullptr, st));
     if (cfg->aux_traj) {
       // quirk C.4: rigid_0_traj / trans_traj of the last step reuse the PREVIOUS prediction (rigid_pred not refreshed)
       CK(cudaMemcpyAsync(L.rigids, L.rigids_pred, R * 7 * sizeof(float), cudaMemcpyDeviceToDevice, st));
@@ -1162,10 +1204,13 @@ static int validate_cfg(const fd_sample_cfg* c) {
   return FD_OK;
 }
 
-static int init_loop_inputs(fd_context* h, const fd_sample_cfg* cfg, const float* res_mask_h, const float* fixed_mask_h, const int32_t* seq_h) {
+static int init_loop_inputs(fd_context* h, const fd_sample_cfg* cfg, const float* res_mask_h, const float* fixed_mask_h, const int32_t* seq_h,
+                            const float* gt_psi_h) {
   LoopBufs& L = h->lb;
   cudaStream_t st = h->stream;
   const long long R = (long long)cfg->B * cfg->N;
+  L.have_gt_psi = gt_psi_h != nullptr;
+  if (gt_psi_h) CK(cudaMemcpyAsync(L.gt_psi, gt_psi_h, R * 2 * 4, cudaMemcpyHostToDevice, st));
   if (res_mask_h) CK(cudaMemcpyAsync(L.res_mask, res_mask_h, R * 4, cudaMemcpyHostToDevice, st));
   else fill_f32_kernel<<<(unsigned)((R + 255) / 256), 256, 0, st>>>(L.res_mask, 1.f, R);
   if (fixed_mask_h) CK(cudaMemcpyAsync(L.fixed_mask, fixed_mask_h, R * 4, cudaMemcpyHostToDevice, st));
@@ -1180,7 +1225,7 @@ extern "C" int fd_sample_host(fd_handle h, const fd_sample_cfg* cfg, const fd_sa
   if (!h || !out) return fail(FD_EINVAL, "fd_sample_host: null argument");
   CKI(validate_cfg(cfg));
   if (!h->weights_loaded) return fail(FD_ESTATE, "fd_sample: weights not loaded");
-  CK(cudaSetDevice(h->device));
+  DevGuard dev_guard(h->device);
   static const fd_sample_in kEmpty = {};
   if (!in) in = &kEmpty;
   const bool inj_prior = in->z_axis != nullptr, inj_steps = in->z_rot != nullptr;
@@ -1191,7 +1236,7 @@ extern "C" int fd_sample_host(fd_handle h, const fd_sample_cfg* cfg, const fd_sa
   CKI(ensure_lb(h, B, N, num_t, cfg->aux_traj, inj_prior || inj_steps));
   LoopBufs& L = h->lb;
   cudaStream_t st = h->stream;
-  CKI(init_loop_inputs(h, cfg, in->res_mask, in->fixed_mask, in->seq_idx));
+  CKI(init_loop_inputs(h, cfg, in->res_mask, in->fixed_mask, in->seq_idx, in->gt_psi));
   if (in->rigids_init) {
     CK(cudaMemcpyAsync(L.rigids, in->rigids_init, R * 7 * 4, cudaMemcpyHostToDevice, st));
   } else if (inj_prior) {
@@ -1229,12 +1274,12 @@ extern "C" int fd_sample_dev(fd_handle h, const fd_sample_cfg* cfg, const float*
   CKI(validate_cfg(cfg));
   if (!h->weights_loaded) return fail(FD_ESTATE, "fd_sample: weights not loaded");
   if (cfg->aux_traj) return fail(FD_EINVAL, "fd_sample_dev: aux_traj is only available through fd_sample_host");
-  CK(cudaSetDevice(h->device));
+  DevGuard dev_guard(h->device);
   const long long R = (long long)cfg->B * cfg->N;
   CKI(ensure_lb(h, cfg->B, cfg->N, cfg->num_t, 0, false));
   LoopBufs& L = h->lb;
   cudaStream_t st = h->stream;
-  CKI(init_loop_inputs(h, cfg, nullptr, nullptr, nullptr));
+  CKI(init_loop_inputs(h, cfg, nullptr, nullptr, nullptr, nullptr));
   if (rigids_init_dev) CK(cudaMemcpyAsync(L.rigids, rigids_init_dev, R * 7 * 4, cudaMemcpyDeviceToDevice, st));
   else CKI(fd_sample_ref(h, R, nullptr, nullptr, nullptr, cfg->seed, cfg->first_sample, cfg->N, L.rigids, st));
   CKI(run_loop(h, cfg, false, gpu_ms, kernel_launches));
@@ -1250,7 +1295,7 @@ extern "C" int fd_sample_dev(fd_handle h, const fd_sample_cfg* cfg, const float*
 // Developer aid (not in the public header): cycle counters of the fused EdgeTransition kernel's roles (CTA 0, last launch).
 extern "C" int fd_debug_tc_profile(fd_handle h, int on, long long* out32) {
   if (!h) return FD_EINVAL;
-  cudaSetDevice(h->device);
+  DevGuard dev_guard(h->device);
   cudaDeviceSynchronize();
   if (on && !g_tc_prof) { cudaMalloc(&g_tc_prof, 32 * sizeof(long long)); cudaMemset(g_tc_prof, 0, 32 * sizeof(long long)); }
   if (out32 && g_tc_prof) cudaMemcpy(out32, g_tc_prof, 32 * sizeof(long long), cudaMemcpyDeviceToHost);
@@ -1296,7 +1341,7 @@ extern "C" int fd_loss_forward(fd_handle h, int B, int N, const fd_loss_in* in, 
     return fail(FD_EINVAL, "fd_loss_forward: null input pointer");
   const size_t smem = (size_t)30 * N * sizeof(float);
   if (smem > 200 * 1024) return fail(FD_EINVAL, "fd_loss_forward: N = %d too long (pair-distance tile needs %zu bytes of shared memory)", N, smem);
-  CK(cudaSetDevice(h->device));
+  DevGuard dev_guard(h->device);
   if (smem > 48 * 1024) CK(cudaFuncSetAttribute(loss_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   // per device
   LossArgs a{};
   a.pred_rot = in->pred_rot_score; a.pred_trans = in->pred_trans_score; a.pred_rigids = in->pred_rigids; a.pred_atom37 = in->pred_atom37;
