@@ -140,7 +140,9 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    state = synthetic_state()
+    from oracle import framediff_oracle as fo      # this arm never touches the product package or its .so
+    state = fo.synthetic_weights(0)
+    args.cpu_steps = max(args.cpu_steps, 10)       # at least 10 denoise steps per bounded sample
     times = []
     last = None
     for i in range(args.warmup + args.steps):
@@ -151,7 +153,9 @@ def run_reference(args):
     cb = dict(last); cb["value"] = v
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "residues/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * args.nres / v, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic (random-init weights, Gaussian/IGSO(3) prior noise)",
+            "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic (random-init weights of the FrameDiff architecture, not weights/paper_weights.pth: throughput-neutral; "
+                    "Gaussian/IGSO(3) prior noise)",
             "config": {"workload": f"1 backbone x N={args.nres} x {args.num_t} denoise steps per step, CPU (bounded sample, extrapolated)",
                        "nres": args.nres, "num_t": args.num_t},
             "cpu_baseline": cb, "e2e": {"value": v, "unit": "residues/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},

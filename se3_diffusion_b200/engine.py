@@ -50,6 +50,8 @@ class FrameDiffEngine:
         self._h = h
         self.set_precision(precision)
         self._weights_version = None
+        self.validate_t = False
+        self.last_gpu_ms = None
 
     def __del__(self):
         try:
@@ -101,9 +103,11 @@ class FrameDiffEngine:
         t_is_f32 = 0 if t_in.dtype == torch.float64 else 1
         f32 = lambda x: torch.as_tensor(x).to(dev, torch.float32).contiguous()
         rigids_t = f32(rig)
-        t64 = t_in.to(dev, torch.float64).contiguous()
-        if bool(((t64 < 0) | (t64 > 1)).any()):
+        # the reference raises ValueError for t outside [0,1] (so3_diffuser.py:194); host tensors are checked for free, device tensors
+        # only on request (validate_t=True) because the check forces a device->host sync per call
+        if (t_in.device.type == "cpu" or self.validate_t) and bool(((t_in < 0) | (t_in > 1)).any()):
             raise ValueError(f"Invalid t={t_in}")
+        t64 = t_in.to(dev, torch.float64).contiguous()
         res_mask, fixed_mask = f32(feats["res_mask"]), f32(feats["fixed_mask"])
         seq_idx = torch.as_tensor(feats["seq_idx"]).to(dev, torch.int32).contiguous()
         sc_ca = f32(feats["sc_ca_t"])
@@ -195,7 +199,7 @@ class FrameDiffEngine:
     def sample(self, B: int, N: int, num_t: int = 500, min_t: float = 0.01, noise_scale: float = 0.1, center: bool = True,
                self_condition: bool = True, aux_traj: bool = False, seed: int = 123, first_sample: int = 0,
                use_graph: bool = True, rigids_init=None, noise: Optional[dict] = None, res_mask=None, fixed_mask=None,
-               seq_idx=None, pinned: bool = True) -> dict:
+               seq_idx=None, pinned: bool = True, gt_psi=None) -> dict:
         """Whole reverse loop through fd_sample_host: HOST buffers in / out (H2D + D2H inside the call).
 
         noise: optional dict of injected numpy draws {z_axis,u_angle,z_trans0,z_rot,z_trans} (float64).
@@ -216,7 +220,7 @@ class FrameDiffEngine:
         noise = noise or {}
         sin = SampleIn(*[_np_ptr(host(noise.get(k), np.float64)) for k in ("z_axis", "u_angle", "z_trans0", "z_rot", "z_trans")],
                        _np_ptr(host(rigids_init, np.float32)), _np_ptr(host(res_mask, np.float32)),
-                       _np_ptr(host(fixed_mask, np.float32)), _np_ptr(host(seq_idx, np.int32)))
+                       _np_ptr(host(fixed_mask, np.float32)), _np_ptr(host(seq_idx, np.int32)), _np_ptr(host(gt_psi, np.float32)))
 
         def out_buf(shape):
             t = torch.empty(shape, dtype=torch.float32, pin_memory=pinned)
@@ -300,13 +304,16 @@ def _inference_fn(self, data_init: dict, num_t: int = 500, min_t: float = 0.01, 
     data_init: the reference's feature dict (rigids_t [B,N,7] or [N,7], res_mask, fixed_mask, seq_idx).  noise="numpy" draws the
     per-step Gaussians from the global numpy RNG in the reference's order (so np.random.seed(...) reproduces the reference's
     trajectory); noise="philox" uses the on-device counter-based generator keyed by (seed, first_sample + b).
-    Returns the reference's dict: prot_traj [+ rigid_traj, trans_traj, psi_pred, rigid_0_traj when aux_traj].
+    Returns the reference's dict: prot_traj [+ rigid_traj, trans_traj, psi_pred, rigid_0_traj when aux_traj].  Deviation (documented in
+    INTEGRATION.md): with aux_traj=False prot_traj holds the final frame only ([1,B,N,37,3]) instead of all num_t frames.
     """
     rig = torch.as_tensor(data_init["rigids_t"]).detach().cpu().float()
     if rig.ndim == 2:
         rig = rig[None]
     B, N = rig.shape[:2]
     opt = lambda k, dt: None if k not in data_init else np.ascontiguousarray(torch.as_tensor(data_init[k]).detach().cpu().numpy().reshape(B, N), dtype=dt)
+    tors = data_init.get("torsion_angles_sin_cos")     # psi imputed on fixed (motif) residues: model/score_network.py:196-199
+    gt_psi = None if tors is None else np.ascontiguousarray(torch.as_tensor(tors).detach().cpu().numpy().reshape(B, N, 7, 2)[:, :, 2, :], dtype=np.float32)
     nz = None
     if noise == "numpy" and num_t > 1:
         zr = np.empty((num_t - 1, B, N, 3)); zx = np.empty((num_t - 1, B, N, 3))
@@ -315,12 +322,13 @@ def _inference_fn(self, data_init: dict, num_t: int = 500, min_t: float = 0.01, 
         nz = {"z_rot": zr, "z_trans": zx}
     out = self.sample(B, N, num_t=num_t, min_t=min_t, noise_scale=noise_scale, center=center, self_condition=self_condition,
                       aux_traj=aux_traj, seed=seed, first_sample=first_sample, rigids_init=rig.numpy(), noise=nz,
-                      res_mask=opt("res_mask", np.float32), fixed_mask=opt("fixed_mask", np.float32), seq_idx=opt("seq_idx", np.int32))
+                      res_mask=opt("res_mask", np.float32), fixed_mask=opt("fixed_mask", np.float32), seq_idx=opt("seq_idx", np.int32),
+                      gt_psi=gt_psi)
     ret = {"prot_traj": out["prot_traj"]}
     if aux_traj:
         ret.update({"rigid_traj": out["rigid_traj"], "trans_traj": out["trans_traj"], "psi_pred": torch.as_tensor(out["psi_pred"]),
                     "rigid_0_traj": out["rigid_0_traj"]})
-    ret["_gpu_ms"] = out["gpu_ms"]
+    self.last_gpu_ms = out["gpu_ms"]      # timing is an attribute, not a key: Sampler.sample tree-maps over the returned dict
     return ret
 
 
@@ -361,7 +369,7 @@ def loss_forward(engine: "FrameDiffEngine", model_out: dict, batch: dict, exp_co
     cfg = LossCfg(*[float(conf[k]) for k, ty in LossCfg._fields_ if ty is C.c_double], int(bool(conf["separate_rot_loss"])),
                   int(bool(diffuse_trans)), int(bool(diffuse_rot)))
     terms = torch.empty((B, 5), dtype=torch.float64, device=dev)
-    check(engine.lib.fd_loss_forward(engine._h, B, N, C.byref(lin), C.byref(cfg), _ptr(terms), None))
+    check(engine.lib.fd_loss_forward(engine._h, B, N, C.byref(lin), C.byref(cfg), _ptr(terms), C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
     n_valid = torch.any(res_mask > 0, dim=-1).sum() + 1e-10
     out = {"batch_rot_loss": terms[:, 0], "batch_trans_loss": terms[:, 1], "batch_bb_atom_loss": terms[:, 2],
            "batch_dist_mat_loss": terms[:, 3], "batch_train_loss": terms[:, 4]}

@@ -44,5 +44,9 @@ def sample_sharded(engine, global_batch: int, nres: int, **kw):
     world = dist.get_world_size() if dist.is_initialized() else 1
     rank = dist.get_rank() if dist.is_initialized() else 0
     first, count = shard_range(global_batch, world, rank)
-    a37, rig, ms, nl = engine.sample_device(count, nres, first_sample=first, **kw)
+    if count == 0:      # more ranks than samples: nothing to run here, but this rank still takes part in the gather
+        dev = engine.device
+        a37, rig, ms, nl = torch.empty(0, nres, 37, 3, device=dev), torch.empty(0, nres, 7, device=dev), 0.0, 0
+    else:
+        a37, rig, ms, nl = engine.sample_device(count, nres, first_sample=first, **kw)
     return gather_samples(a37, global_batch), gather_samples(rig, global_batch), ms, nl

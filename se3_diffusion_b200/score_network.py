@@ -147,8 +147,22 @@ class ScoreNetwork(nn.Module):
         self._loaded_version = None
 
     # ---- engine management ---------------------------------------------------------------------------------------------
-    def _weights_version(self):
-        return tuple(p._version for p in self.parameters()) + (id(next(self.parameters()).data_ptr),)
+    def _weights_key(self):
+        """Changes whenever a parameter may have changed: in-place writes bump `_version`; `p.data = ...` / `.to()` / re-allocation change
+        `data_ptr()`.  Writes through `p.data.copy_()` change neither — call `invalidate_weights()` after such utilities (EMA swaps)."""
+        return tuple((p._version, p.data_ptr()) for p in self.parameters())
+
+    def invalidate_weights(self):
+        """Force the next forward to re-pack the device weight arena from the module's parameters."""
+        self._loaded_version = None
+
+    def _apply(self, fn, *a, **k):
+        self._loaded_version = None
+        return super()._apply(fn, *a, **k)
+
+    def load_state_dict(self, *a, **k):
+        self._loaded_version = None
+        return super().load_state_dict(*a, **k)
 
     def engine(self, device=None) -> FrameDiffEngine:
         dev = device if device is not None else next(self.parameters()).device
@@ -159,7 +173,7 @@ class ScoreNetwork(nn.Module):
                 self.diffuser.bind_engine(self._engine_obj)
         if self._engine_obj.precision != self.precision:
             self._engine_obj.set_precision(self.precision)
-        ver = tuple(p._version for p in self.parameters())
+        ver = self._weights_key()
         if ver != self._loaded_version:          # parameters changed (load_state_dict / optimiser step): repack the device arena
             self._engine_obj.load_weights(self.state_dict())
             self._loaded_version = ver
