@@ -23,9 +23,15 @@ struct GemmArgs {
   // edge-row broadcast adds: global row g = row_offset + m -> b = g / (nres*nres), i = (g / nres) % nres, j = g % nres
   const float* rowadd_i = nullptr; const float* rowadd_j = nullptr; int ld_rowadd = 0; int nres = 0; long long row_offset = 0;
   int vecA = 0, vecB = 0;               // 16-byte vector loads allowed (pointer, ld and batch strides 4-float aligned)
+  // training-path extensions
+  const float* relumask = nullptr; int ldm = 0;   // v = relumask[m][n] > 0 ? v : 0 (backward of a ReLU whose OUTPUT is relumask), applied last
+  int splits = 1;                       // split-K: blockIdx.z = batch * splits + split, partial sums combined with atomicAdd (needs atomic = 1)
+  int atomic = 0;                       // C[m][n] += alpha*acc through atomicAdd (gradient accumulation); bias/rowadd/relu/residual ignored
 };
 
-template <int BM, int BN, int TM, int TN, bool B_KMAJOR>
+// A_KMAJOR = true : A is A[m][k] (row-major activations, K contiguous)
+// A_KMAJOR = false: A is At[k][m] (M contiguous) — weight gradients dW[m][n] = sum_k dY[k][m] X[k][n] read both operands untransposed
+template <int BM, int BN, int TM, int TN, bool B_KMAJOR, bool A_KMAJOR = true>
 __global__ void __launch_bounds__(256) gemm_kernel(const GemmArgs g) {
   constexpr int BK = 8;
   constexpr int LDA_S = BM + 4, LDB_S = BN + 4;
@@ -34,12 +40,21 @@ __global__ void __launch_bounds__(256) gemm_kernel(const GemmArgs g) {
   __shared__ __align__(16) float Bs[2][BK][LDB_S];
 
   const int tid = threadIdx.x;
-  const int z = blockIdx.z, z0 = z / g.nb1, z1 = z % g.nb1;
+  const int zs = blockIdx.z / g.splits, split = blockIdx.z - zs * g.splits;
+  const int z = zs, z0 = z / g.nb1, z1 = z % g.nb1;
   const float* __restrict__ A = g.A + z0 * g.sA0 + z1 * g.sA1;
   const float* __restrict__ B = g.B + z0 * g.sB0 + z1 * g.sB1;
   float* __restrict__ C = g.C + z0 * g.sC0 + z1 * g.sC1;
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
-  const int M = g.M, N = g.N, K = g.K;
+  const int M = g.M, N = g.N;
+  // split-K: this CTA covers k in [kbeg, K)
+  int kbeg = 0, K = g.K;
+  if (g.splits > 1) {
+    const int per = ((g.K + g.splits - 1) / g.splits + BK - 1) / BK * BK;
+    kbeg = split * per;
+    K = min(g.K, kbeg + per);
+    if (kbeg >= K) return;
+  }
 
   constexpr int TX = BN / TN;           // thread columns
   const int tx = tid % TX, ty = tid / TX;
@@ -54,16 +69,31 @@ __global__ void __launch_bounds__(256) gemm_kernel(const GemmArgs g) {
       const int idx = tid + it * 256;
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
       if (idx < A_F4) {
-        const int row = idx / (BK / 4), kq = (idx % (BK / 4)) * 4;
-        const int m = m0 + row, k = k0 + kq;
-        if (m < M) {
-          const float* p = A + (long long)m * g.lda + k;
-          if (g.vecA && k + 3 < K) v = *reinterpret_cast<const float4*>(p);
-          else {
-            if (k < K) v.x = p[0];
-            if (k + 1 < K) v.y = p[1];
-            if (k + 2 < K) v.z = p[2];
-            if (k + 3 < K) v.w = p[3];
+        if (A_KMAJOR) {
+          const int row = idx / (BK / 4), kq = (idx % (BK / 4)) * 4;
+          const int m = m0 + row, k = k0 + kq;
+          if (m < M) {
+            const float* p = A + (long long)m * g.lda + k;
+            if (g.vecA && k + 3 < K) v = *reinterpret_cast<const float4*>(p);
+            else {
+              if (k < K) v.x = p[0];
+              if (k + 1 < K) v.y = p[1];
+              if (k + 2 < K) v.z = p[2];
+              if (k + 3 < K) v.w = p[3];
+            }
+          }
+        } else {
+          const int kr = idx / (BM / 4), mq = (idx % (BM / 4)) * 4;
+          const int k = k0 + kr, m = m0 + mq;
+          if (k < K) {
+            const float* p = A + (long long)k * g.lda + m;
+            if (g.vecA && m + 3 < M) v = *reinterpret_cast<const float4*>(p);
+            else {
+              if (m < M) v.x = p[0];
+              if (m + 1 < M) v.y = p[1];
+              if (m + 2 < M) v.z = p[2];
+              if (m + 3 < M) v.w = p[3];
+            }
           }
         }
       }
@@ -110,9 +140,14 @@ __global__ void __launch_bounds__(256) gemm_kernel(const GemmArgs g) {
     for (int it = 0; it < A_PER; ++it) {
       const int idx = tid + it * 256;
       if (idx < A_F4) {
-        const int row = idx / (BK / 4), kq = (idx % (BK / 4)) * 4;
-        As[buf][kq + 0][row] = ra[it].x; As[buf][kq + 1][row] = ra[it].y;
-        As[buf][kq + 2][row] = ra[it].z; As[buf][kq + 3][row] = ra[it].w;
+        if (A_KMAJOR) {
+          const int row = idx / (BK / 4), kq = (idx % (BK / 4)) * 4;
+          As[buf][kq + 0][row] = ra[it].x; As[buf][kq + 1][row] = ra[it].y;
+          As[buf][kq + 2][row] = ra[it].z; As[buf][kq + 3][row] = ra[it].w;
+        } else {
+          const int kr = idx / (BM / 4), mq = (idx % (BM / 4)) * 4;
+          *reinterpret_cast<float4*>(&As[buf][kr][mq]) = ra[it];
+        }
       }
     }
 #pragma unroll
@@ -141,13 +176,13 @@ __global__ void __launch_bounds__(256) gemm_kernel(const GemmArgs g) {
   constexpr int RG = TM / 4, CG = TN / 4;
   constexpr int RSTRIDE = BM / RG, CSTRIDE = BN / CG;
 
-  const int nk = (K + BK - 1) / BK;
-  load_tiles(0);
+  const int nk = (K - kbeg + BK - 1) / BK;
+  load_tiles(kbeg);
   store_tiles(0);
   __syncthreads();
   for (int kt = 0; kt < nk; ++kt) {
     const int buf = kt & 1;
-    if (kt + 1 < nk) load_tiles((kt + 1) * BK);
+    if (kt + 1 < nk) load_tiles(kbeg + (kt + 1) * BK);
 #pragma unroll
     for (int k = 0; k < BK; ++k) {
       float a[TM], b[TN];
@@ -197,6 +232,7 @@ __global__ void __launch_bounds__(256) gemm_kernel(const GemmArgs g) {
         const int n = nb + jj;
         if (n >= N) continue;
         float v = g.alpha * acc[i][c * 4 + jj];
+        if (g.atomic) { atomicAdd(C + (long long)m * g.ldc + n, v); continue; }
         if (g.bias) v += g.bias[n];
         if (pi) v += pi[n] + pj[n];
         float* cp = C + (long long)m * g.ldc + n;
@@ -204,6 +240,7 @@ __global__ void __launch_bounds__(256) gemm_kernel(const GemmArgs g) {
         if (g.relu) v = fmaxf(v, 0.f);
         v *= rm;
         if (R) v += R[(long long)m * g.ldr + n];
+        if (g.relumask && !(g.relumask[(long long)m * g.ldm + n] > 0.f)) v = 0.f;
         *cp = v;
       }
     }
@@ -211,11 +248,25 @@ __global__ void __launch_bounds__(256) gemm_kernel(const GemmArgs g) {
 }
 
 // Host-side launcher: picks the 128x128 (8x8 per thread) tile for big problems, 64x64 (4x4) otherwise.
-inline cudaError_t launch_gemm(GemmArgs g, bool b_kmajor, cudaStream_t st) {
+inline cudaError_t launch_gemm(GemmArgs g, bool b_kmajor, cudaStream_t st, bool a_kmajor = true) {
   auto al4 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
   g.vecA = al4(g.A) && g.lda % 4 == 0 && g.sA0 % 4 == 0 && g.sA1 % 4 == 0;
   g.vecB = al4(g.B) && g.ldb % 4 == 0 && g.sB0 % 4 == 0 && g.sB1 % 4 == 0;
-  const int nbatch = g.nb0 * g.nb1;
+  if (g.splits < 1) g.splits = 1;
+  if (g.splits > 1 && !g.atomic) return cudaErrorInvalidValue;
+  const int nbatch = g.nb0 * g.nb1 * g.splits;
+  if (!a_kmajor) {   // weight-gradient form (A and B both read along their contiguous dimension)
+    if (b_kmajor) return cudaErrorInvalidValue;
+    const bool big = g.M >= 96 && g.N >= 96;
+    if (big) {
+      dim3 grid((g.N + 127) / 128, (g.M + 127) / 128, nbatch);
+      gemm_kernel<128, 128, 8, 8, false, false><<<grid, 256, 0, st>>>(g);
+    } else {
+      dim3 grid((g.N + 63) / 64, (g.M + 63) / 64, nbatch);
+      gemm_kernel<64, 64, 4, 4, false, false><<<grid, 256, 0, st>>>(g);
+    }
+    return cudaGetLastError();
+  }
   const bool big = (long long)g.M * g.N >= 128LL * 128 * 64 && g.N >= 96 && g.M >= 128;
   if (big) {
     dim3 grid((g.N + 127) / 128, (g.M + 127) / 128, nbatch);

@@ -42,10 +42,12 @@ def _assert_elementwise(a, b, rtol, name, frac=0.999):
     assert (err <= 5 * bound).all(), f"{name}: {int((err > 5 * bound).sum())} elements beyond 5x the elementwise bound; worst {err.max():.3e}"
 
 
-def _check_forward(out, ref, t, rigids_t, tol=TOL, name=""):
+def _check_forward(out, ref, t, rigids_t, tol=TOL, name="", psi_tol=None):
+    """psi_tol: psi = u/|u| of a 2-vector — where |u| is small the normalisation amplifies the element error of the hidden state, so
+    the split-bf16 mode (1e-5 element error) gets 5e-4 on the torsion itself; the O-atom coordinates it places stay under `tol`."""
     o = {k: v.detach().cpu().numpy() for k, v in out.items()}
     for k in ("psi", "trans_score", "atom37", "atom14"):
-        assert_close(o[k], ref[k], 0, norm_rel=tol, name=f"{name}{k}")
+        assert_close(o[k], ref[k], 0, norm_rel=(psi_tol or tol) if k == "psi" else tol, name=f"{name}{k}")
     for k in ("trans_score", "atom37"):
         _assert_elementwise(o[k], ref[k], tol, name + k + " (elementwise)")
     assert_close(quat_align(o["rigids"][..., :4], ref["rigids"][..., :4]), ref["rigids"][..., :4], 0, atol=20 * tol, name=name + "quat")
@@ -362,7 +364,8 @@ def test_forward_vs_oracle_bench_shapes(prec, B, N):
     with torch.no_grad():
         ref = fo.score_network_forward(fo.as_torch_weights(fo.synthetic_weights(0)), f)
     out = engine(prec).forward(f)
-    _check_forward(out, {k: v.numpy() for k, v in ref.items()}, f["t"].numpy(), f["rigids_t"].numpy(), name=f"{prec} B{B} N{N} ")
+    _check_forward(out, {k: v.numpy() for k, v in ref.items()}, f["t"].numpy(), f["rigids_t"].numpy(), name=f"{prec} B{B} N{N} ",
+                   psi_tol=None if prec == "fp32" else 5e-4)
 
 
 @pytest.mark.parametrize("prec", ["fp32", "bf16x3"])
