@@ -209,7 +209,7 @@ int fd_debug_tc_profile(fd_handle h, int on, long long* out32);
  * noised batch: terms[b] = { rot_loss, trans_loss, bb_atom_loss, dist_mat_loss, sum } (aux_data's `batch_*` entries; the
  * caller divides their sums by the number of non-empty samples, :662).  All pointers device memory.  Scores, scalings,
  * rigids_0 and t are fp64 (as the reference's batch / model outputs are), frames, atoms, masks and psi fp32.
- * The backward pass / optimizer step are not part of this library yet. */
+ * Gradients: fd_loss_backward below. */
 typedef struct {
   const double* pred_rot_score;    /* [B,N,3]  model_out['rot_score'] */
   const double* pred_trans_score;  /* [B,N,3] */
@@ -231,6 +231,51 @@ typedef struct {                   /* config/base.yaml:104-115 + diffuser.diffus
   int separate_rot_loss, diffuse_trans, diffuse_rot;
 } fd_loss_cfg;
 int fd_loss_forward(fd_handle h, int B, int N, const fd_loss_in* in, const fd_loss_cfg* cfg, double* terms_dev /* [B,5] */, void* stream);
+
+/* ---- training step -------------------------------------------------------------------------- */
+/* The reference has no backward code: Experiment.update_fn (experiments/train_se3_diffusion.py:320-326) calls loss.backward() and torch
+ * autograd differentiates loss_fn (:524-693) and ScoreNetwork.forward.  Here that derivative is hand-written CUDA.
+ * Parameters and gradients live in two flat fp32 device arenas owned by the CALLER, laid out in the state_dict's own order and shapes:
+ * parameter i occupies [fd_train_param_offset(i), +fd_param_numel(i)) (offsets are 256-byte aligned; fd_train_arena_floats() floats
+ * in total; padding floats are never read).  The nn.Module's parameters / .grad tensors are views into these arenas, so
+ * torch.optim.Adam, DDP or a plain NCCL all-reduce over slices of the gradient arena work on them directly.  The backward
+ * ACCUMULATES into the gradient arena (zero it per step, like optimizer.zero_grad).  The 10 parameters the reference never uses
+ * (linear_rbf x4 blocks, torsion_pred.linear_3) receive no gradient. */
+int64_t fd_train_arena_floats(void);
+int64_t fd_train_param_offset(int i);
+int fd_train_bind(fd_handle h, float* params_dev, float* grads_dev);
+/* Training-mode forward: same inputs / outputs as fd_forward, computed from the bound parameter arena with the semantics torch
+ * applies whenever autograd records (the float key-padding mask is ADDED to the sequence-attention logits, model/ipa_pytorch.py:636,
+ * SURVEY Appendix C.2); every activation the backward needs is kept on a tape owned by the handle (fd_train_release frees it).
+ * The input pointers must stay valid until the matching fd_train_backward has run. */
+int fd_train_forward(fd_handle h, int B, int N, const fd_forward_in* in, const fd_forward_out* out, void* stream);
+/* Gradients w.r.t. the model outputs (device pointers, any may be NULL = zero): what autograd hands to the network's outputs. */
+typedef struct {
+  const double* d_rot_score;    /* [B,N,3] */
+  const double* d_trans_score;  /* [B,N,3] */
+  const float* d_rigids;        /* [B,N,7] */
+  const float* d_atom37;        /* [B,N,37,3] (atoms 0..4 are functions of the frames / psi, the rest are constant zeros) */
+  const float* d_atom14;        /* [B,N,14,3] */
+  const float* d_psi;           /* [B,N,2] */
+} fd_train_grads;
+/* Backward of the last fd_train_forward in four stages — 0: torsion head + trunk block 3, 1: block 2, 2: block 1, 3: block 0 + the
+ * embedders — so that the caller can all-reduce a finished gradient bucket (a contiguous slice of the arena) while the next stage
+ * computes.  Stages must run in order 0..3; (0,3) runs the whole backward. */
+int fd_train_backward(fd_handle h, const fd_train_grads* dout, int stage_first, int stage_last, void* stream);
+int fd_train_release(fd_handle h);
+/* d total_loss / d model outputs for Experiment.loss_fn (train_se3_diffusion.py:538-680; total_loss = sum_b batch_loss[b] / #non-empty
+ * samples): the gradient fd_train_backward starts from when the loss is not computed by torch. */
+typedef struct {
+  double* d_rot_score;          /* [B,N,3] */
+  double* d_trans_score;        /* [B,N,3] */
+  float* d_rigids;              /* [B,N,7] */
+  float* d_atom37;              /* [B,N,37,3] */
+} fd_train_grads_out;
+int fd_loss_backward(fd_handle h, int B, int N, const fd_loss_in* in, const fd_loss_cfg* cfg, const fd_train_grads_out* out, void* stream);
+/* torch.optim.Adam (defaults of the reference, train_se3_diffusion.py:139-141: no weight decay, no amsgrad) over n contiguous floats;
+ * step counts from 1; grads are multiplied by grad_scale first (1/world_size after a SUM all-reduce). */
+int fd_adam_step(fd_handle h, float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, double lr, double beta1,
+                 double beta2, double eps, int64_t step, double grad_scale, void* stream);
 
 /* ---- downstream data format: PDB text of sampled backbones ---------------------------------- */
 /* Host-only (no CUDA call): the text analysis/utils.py:39-77 write_prot_to_pdb + data/protein.py:146-219 to_pdb produce

@@ -25,6 +25,14 @@ class LossCfg(C.Structure):
                [(k, C.c_int) for k in ("separate_rot_loss", "diffuse_trans", "diffuse_rot")]
 
 
+class TrainGrads(C.Structure):
+    _fields_ = [(k, c_voidp) for k in ("d_rot_score", "d_trans_score", "d_rigids", "d_atom37", "d_atom14", "d_psi")]
+
+
+class TrainGradsOut(C.Structure):
+    _fields_ = [(k, c_voidp) for k in ("d_rot_score", "d_trans_score", "d_rigids", "d_atom37")]
+
+
 class ForwardOut(C.Structure):
     _fields_ = [("rot_score", c_voidp), ("trans_score", c_voidp), ("psi", c_voidp), ("rigids", c_voidp),
                 ("atom37", c_voidp), ("atom14", c_voidp)]
@@ -82,6 +90,15 @@ SYMBOLS = {
     "fd_forward_flops": (C.c_int64, [C.c_int, C.c_int, C.c_int]),
     "fd_debug_tc_profile": (C.c_int, [c_voidp, C.c_int, C.POINTER(C.c_longlong)]),
     "fd_loss_forward": (C.c_int, [c_voidp, C.c_int, C.c_int, c_voidp, c_voidp, c_voidp, c_voidp]),
+    "fd_train_arena_floats": (C.c_int64, []),
+    "fd_train_param_offset": (C.c_int64, [C.c_int]),
+    "fd_train_bind": (C.c_int, [c_voidp, c_voidp, c_voidp]),
+    "fd_train_forward": (C.c_int, [c_voidp, C.c_int, C.c_int, C.POINTER(ForwardIn), C.POINTER(ForwardOut), c_voidp]),
+    "fd_train_backward": (C.c_int, [c_voidp, C.POINTER(TrainGrads), C.c_int, C.c_int, c_voidp]),
+    "fd_train_release": (C.c_int, [c_voidp]),
+    "fd_loss_backward": (C.c_int, [c_voidp, C.c_int, C.c_int, c_voidp, c_voidp, C.POINTER(TrainGradsOut), c_voidp]),
+    "fd_adam_step": (C.c_int, [c_voidp, c_voidp, c_voidp, c_voidp, c_voidp, C.c_int64, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int64,
+                               C.c_double, c_voidp]),
     "fd_format_pdb": (C.c_int, [c_voidp, C.c_int, C.POINTER(C.c_ubyte), C.POINTER(C.c_int), c_f64p, C.c_int, C.c_int, C.c_void_p, C.c_size_t,
                                 C.POINTER(C.c_size_t)]),
 }

@@ -12,6 +12,7 @@
 #include "fd_common.cuh"
 #include "fd_gemm.cuh"
 #include "fd_kernels.cuh"
+#include "fd_train.cuh"
 #include "fd_weights.h"
 #include "fd_tc.cuh"
 
@@ -115,9 +116,11 @@ struct fd_context {
     double noise_scale = 0; uint64_t seed = 0; long long first_sample = 0;
     const void *ws_base = nullptr, *lb_base = nullptr, *warena = nullptr;
   } gc;
+  struct fd_train_state* train = nullptr;   // training step state (bound arenas + tape), fd_train_host.cuh
   cudaEvent_t ev_fwd = nullptr;      // recorded after fd_forward on the caller's stream; the sampling stream waits on it (shared workspace)
   bool fwd_pending = false;
 };
+static void free_train(fd_context* h);
 static void free_graph(fd_context* h) {
   if (h->gc.exec) cudaGraphExecDestroy(h->gc.exec);
   if (h->gc.graph) cudaGraphDestroy(h->gc.graph);
@@ -257,6 +260,7 @@ extern "C" int fd_destroy(fd_handle h) {
   tc_free_weights(h->tcw);
   cudaFree(h->d_sigma_grid); cudaFree(h->d_cdf_t1); cudaFree(h->d_omega); cudaFree(h->d_sched1);
   if (h->d_t_tmp) cudaFree(h->d_t_tmp);
+  free_train(h);
   if (h->ev_fwd) cudaEventDestroy(h->ev_fwd);
   cudaStreamDestroy(h->stream);
   delete h;
@@ -1286,6 +1290,100 @@ extern "C" int fd_sample_dev(fd_handle h, const fd_sample_cfg* cfg, const float*
   if (atom37_dev) CK(cudaMemcpyAsync(atom37_dev, L.atom37, R * 111 * 4, cudaMemcpyDeviceToDevice, st));
   if (rigids_dev) CK(cudaMemcpyAsync(rigids_dev, L.rigids, R * 7 * 4, cudaMemcpyDeviceToDevice, st));
   CK(cudaStreamSynchronize(st));
+  return FD_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// training step (include/framediff_b200.h: fd_train_*)
+// ------------------------------------------------------------------------------------------------------------------
+#include "fd_train_host.cuh"
+
+static fd_train_state* train_state(fd_context* h) {
+  if (!h->train) h->train = new fd_train_state();
+  return h->train;
+}
+static void free_train(fd_context* h) {
+  if (!h->train) return;
+  free_tape(h->train->tape);
+  delete h->train;
+  h->train = nullptr;
+}
+extern "C" int64_t fd_train_arena_floats(void) { return arena_layout().total; }
+extern "C" int64_t fd_train_param_offset(int i) {
+  const auto& L = arena_layout();
+  return (i < 0 || i >= (int)L.off.size()) ? FD_EINVAL : L.off[i];
+}
+extern "C" int fd_train_bind(fd_handle h, float* params, float* grads) {
+  if (!h || !params || !grads) return fail(FD_EINVAL, "fd_train_bind: null argument");
+  fd_train_state* S = train_state(h);
+  S->P = params; S->G = grads;
+  S->tape.valid = false;
+  return FD_OK;
+}
+extern "C" int fd_train_forward(fd_handle h, int B, int N, const fd_forward_in* in, const fd_forward_out* out, void* stream) {
+  if (!h || !in || !out) return fail(FD_EINVAL, "fd_train_forward: null argument");
+  if (!h->train || !h->train->P) return fail(FD_ESTATE, "fd_train_forward: no parameter arena bound (fd_train_bind)");
+  if (B <= 0 || N <= 0) return fail(FD_EINVAL, "fd_train_forward: B=%d N=%d", B, N);
+  if (!in->rigids_t || !in->t || !in->res_mask || !in->fixed_mask || !in->seq_idx || !in->sc_ca_t)
+    return fail(FD_EINVAL, "fd_train_forward: a required input pointer is NULL");
+  if (!out->rot_score || !out->trans_score || !out->psi || !out->rigids) return fail(FD_EINVAL, "fd_train_forward: a required output pointer is NULL");
+  DevGuard dev_guard(h->device);
+  return train_forward_impl(h, h->train, B, N, in, out, (cudaStream_t)stream);
+}
+extern "C" int fd_train_backward(fd_handle h, const fd_train_grads* dout, int stage_first, int stage_last, void* stream) {
+  if (!h || !dout) return fail(FD_EINVAL, "fd_train_backward: null argument");
+  if (!h->train || !h->train->G) return fail(FD_ESTATE, "fd_train_backward: no gradient arena bound (fd_train_bind)");
+  if (stage_first < 0 || stage_last >= NBLK || stage_first > stage_last) return fail(FD_EINVAL, "fd_train_backward: stages %d..%d", stage_first, stage_last);
+  DevGuard dev_guard(h->device);
+  return train_backward_impl(h, h->train, dout, stage_first, stage_last, (cudaStream_t)stream);
+}
+extern "C" int fd_train_release(fd_handle h) {
+  if (!h) return FD_EINVAL;
+  DevGuard dev_guard(h->device);
+  cudaDeviceSynchronize();
+  free_train(h);
+  return FD_OK;
+}
+extern "C" int fd_loss_backward(fd_handle h, int B, int N, const fd_loss_in* in, const fd_loss_cfg* cfg, const fd_train_grads_out* out, void* stream) {
+  if (!h || !in || !cfg || !out || B < 1 || N < 1) return fail(FD_EINVAL, "fd_loss_backward: bad arguments");
+  if (!out->d_rot_score || !out->d_trans_score || !out->d_rigids || !out->d_atom37) return fail(FD_EINVAL, "fd_loss_backward: null output pointer");
+  if (!in->pred_rot_score || !in->pred_trans_score || !in->pred_rigids || !in->pred_atom37 || !in->gt_rot_score || !in->gt_trans_score ||
+      !in->rot_score_scaling || !in->trans_score_scaling || !in->rigids_0 || !in->t || !in->res_mask || !in->fixed_mask || !in->gt_psi)
+    return fail(FD_EINVAL, "fd_loss_backward: null input pointer");
+  const size_t smem = (size_t)240 * N;
+  if (smem > 200 * 1024) return fail(FD_EINVAL, "fd_loss_backward: N = %d too long", N);
+  DevGuard dev_guard(h->device);
+  if (smem > 48 * 1024) CK(cudaFuncSetAttribute(loss_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  // number of samples with a non-empty mask (train_se3_diffusion.py:662) — a host value: the masks are inputs the caller just uploaded
+  std::vector<float> hm((size_t)B * N);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CK(cudaMemcpyAsync(hm.data(), in->res_mask, hm.size() * sizeof(float), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  int nvalid = 0;
+  for (int b = 0; b < B; ++b) { bool any = false; for (int n = 0; n < N; ++n) any |= hm[(size_t)b * N + n] != 0.f; nvalid += any; }
+  LossBwdArgs a{};
+  a.pred_rot = in->pred_rot_score; a.pred_trans = in->pred_trans_score; a.pred_rigids = in->pred_rigids; a.pred_atom37 = in->pred_atom37;
+  a.gt_rot = in->gt_rot_score; a.gt_trans = in->gt_trans_score; a.rot_scaling = in->rot_score_scaling; a.trans_scaling = in->trans_score_scaling;
+  a.rigids_0 = in->rigids_0; a.t = in->t; a.res_mask = in->res_mask; a.fixed_mask = in->fixed_mask; a.gt_psi = in->gt_psi;
+  a.trans_loss_weight = cfg->trans_loss_weight; a.rot_loss_weight = cfg->rot_loss_weight; a.rot_loss_t_threshold = cfg->rot_loss_t_threshold;
+  a.trans_x0_threshold = cfg->trans_x0_threshold; a.coordinate_scaling = cfg->coordinate_scaling; a.bb_atom_loss_weight = cfg->bb_atom_loss_weight;
+  a.bb_atom_loss_t_filter = cfg->bb_atom_loss_t_filter; a.dist_mat_loss_weight = cfg->dist_mat_loss_weight;
+  a.dist_mat_loss_t_filter = cfg->dist_mat_loss_t_filter; a.aux_loss_weight = cfg->aux_loss_weight;
+  a.separate_rot_loss = cfg->separate_rot_loss; a.diffuse_trans = cfg->diffuse_trans; a.diffuse_rot = cfg->diffuse_rot;
+  a.inv_nvalid = 1.0 / ((double)nvalid + 1e-10);
+  a.d_rot = out->d_rot_score; a.d_trans = out->d_trans_score; a.d_rigids = out->d_rigids; a.d_atom37 = out->d_atom37; a.N = N;
+  loss_backward_kernel<<<B, 256, smem, st>>>(a);
+  CK(cudaGetLastError());
+  return FD_OK;
+}
+extern "C" int fd_adam_step(fd_handle h, float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, double lr, double beta1,
+                            double beta2, double eps, int64_t step, double grad_scale, void* stream) {
+  if (!h || !params || !grads || !exp_avg || !exp_avg_sq || n < 1 || step < 1) return fail(FD_EINVAL, "fd_adam_step: bad arguments");
+  DevGuard dev_guard(h->device);
+  const double bc1 = 1.0 - pow(beta1, (double)step), bc2 = 1.0 - pow(beta2, (double)step);
+  adam_kernel<<<(unsigned)((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(params, grads, exp_avg, exp_avg_sq, n, (float)lr, (float)beta1,
+                                                                                          (float)beta2, (float)eps, (float)bc1, (float)bc2, (float)grad_scale);
+  CK(cudaGetLastError());
   return FD_OK;
 }
 

@@ -380,7 +380,7 @@ __global__ void __launch_bounds__(256) ipa_edge_kernel(
     const ZRef z, float* __restrict__ L, const float* __restrict__ qp, const float* __restrict__ kp,
     const float* __restrict__ res_mask, const float* __restrict__ Wb, const float* __restrict__ bb,
     const float* __restrict__ gamma, const float* __restrict__ WdT, const float* __restrict__ bd,
-    float* __restrict__ feats, int N, int Np) {
+    float* __restrict__ feats, int N, int Np, float* __restrict__ zbar_out = nullptr /* [B*N,H,128]: kept by the training path */) {
   extern __shared__ __align__(16) float sm[];
   float* lg = sm;                         // [H][Np]
   float* qs = lg + H * Np;                // [192]
@@ -514,6 +514,9 @@ __global__ void __launch_bounds__(256) ipa_edge_kernel(
 #pragma unroll 8
     for (int c = 0; c < C_Z; ++c) acc = fmaf(WdT[c * 32 + d], z0[c] + z1[c], acc);
     feats[rowi * IPA_FEAT + (H * C_HID + 4 * H * PV) + h * 32 + d] = acc;
+  }
+  if (zbar_out) {
+    for (int idx = tid; idx < H * C_Z; idx += 256) zbar_out[rowi * (H * C_Z) + idx] = zb[idx] + zb[H * C_Z + idx];
   }
 }
 

@@ -382,3 +382,120 @@ def loss_forward(engine: "FrameDiffEngine", model_out: dict, batch: dict, exp_co
 
 
 FrameDiffEngine.loss_forward = loss_forward
+
+
+# ---- training step (SURVEY rows a27-a28; include/framediff_b200.h fd_train_*) ---------------------------------------------------------
+def arena_layout():
+    """[(name, shape, float offset)] of the flat parameter / gradient arenas and their total length in floats."""
+    lib = _lib.load()
+    sch = param_schema()
+    return [(n, s, int(lib.fd_train_param_offset(i))) for i, (n, s) in enumerate(sch)], int(lib.fd_train_arena_floats())
+
+
+def flat_from_state(state: Dict[str, "np.ndarray | torch.Tensor"], device) -> torch.Tensor:
+    """Packs a state_dict into a new flat fp32 arena on `device` (padding zero)."""
+    lay, total = arena_layout()
+    flat = torch.zeros(total, dtype=torch.float32, device=device)
+    state = {(k[7:] if k.startswith("module.") else k): v for k, v in state.items()}
+    for name, shape, off in lay:
+        v = torch.as_tensor(np.asarray(state[name]) if not torch.is_tensor(state[name]) else state[name]).detach().to(device, torch.float32)
+        if tuple(v.shape) != tuple(shape):
+            raise ValueError(f"parameter {name}: shape {tuple(v.shape)} != {shape}")
+        flat[off:off + v.numel()] = v.reshape(-1)
+    return flat
+
+
+def views_of(flat: torch.Tensor) -> Dict[str, torch.Tensor]:
+    lay, _ = arena_layout()
+    return {name: flat[off:off + int(np.prod(shape))].view(shape) for name, shape, off in lay}
+
+
+def _train_bind(self, params: torch.Tensor, grads: torch.Tensor):
+    _, total = arena_layout()
+    for t in (params, grads):
+        if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and t.numel() == total and t.device == self.device):
+            raise ValueError("fd_train_bind needs two contiguous fp32 CUDA tensors of arena_layout()[1] floats on the engine's device")
+    check(self.lib.fd_train_bind(self._h, _ptr(params), _ptr(grads)))
+    self._train_arenas = (params, grads)
+
+
+def _train_forward(self, feats: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+    """ScoreNetwork.forward in training mode (autograd semantics of the sequence attention); keeps the tape for train_backward."""
+    dev = self.device
+    rig = feats["rigids_t"]
+    B, N = rig.shape[0], rig.shape[1]
+    t_in = torch.as_tensor(feats["t"])
+    t_is_f32 = 0 if t_in.dtype == torch.float64 else 1
+    if t_in.device.type == "cpu" and bool(((t_in < 0) | (t_in > 1)).any()):
+        raise ValueError(f"Invalid t={t_in}")
+    f32 = lambda x: torch.as_tensor(x).to(dev, torch.float32).contiguous()
+    tors = feats.get("torsion_angles_sin_cos")
+    keep = dict(rigids_t=f32(rig), t=t_in.to(dev, torch.float64).contiguous(), res_mask=f32(feats["res_mask"]), fixed_mask=f32(feats["fixed_mask"]),
+                seq_idx=torch.as_tensor(feats["seq_idx"]).to(dev, torch.int32).contiguous(), sc_ca=f32(feats["sc_ca_t"]),
+                gt_psi=f32(torch.as_tensor(tors)[..., 2, :]) if tors is not None else None)
+    out = {"rot_score": torch.empty(B, N, 3, device=dev, dtype=torch.float64), "trans_score": torch.empty(B, N, 3, device=dev, dtype=torch.float64),
+           "psi": torch.empty(B, N, 2, device=dev, dtype=torch.float32), "rigids": torch.empty(B, N, 7, device=dev, dtype=torch.float32),
+           "atom37": torch.empty(B, N, 37, 3, device=dev, dtype=torch.float32), "atom14": torch.empty(B, N, 14, 3, device=dev, dtype=torch.float32)}
+    fin = ForwardIn(_ptr(keep["rigids_t"]), _ptr(keep["t"]), t_is_f32, None, _ptr(keep["res_mask"]), _ptr(keep["fixed_mask"]), _ptr(keep["seq_idx"]),
+                    _ptr(keep["sc_ca"]), _ptr(keep["gt_psi"]))
+    fout = ForwardOut(*[_ptr(out[k]) for k in ("rot_score", "trans_score", "psi", "rigids", "atom37", "atom14")])
+    st = torch.cuda.current_stream(dev)
+    check(self.lib.fd_train_forward(self._h, B, N, C.byref(fin), C.byref(fout), C.c_void_p(st.cuda_stream)))
+    self._train_keep = keep            # inputs must outlive the backward
+    if t_is_f32:
+        out["trans_score"] = out["trans_score"].to(torch.float32)
+    return out
+
+
+def _train_backward(self, dout: Dict[str, Optional[torch.Tensor]], stage_first: int = 0, stage_last: int = 3):
+    """Backward of the last train_forward from the gradients w.r.t. its outputs (missing keys = zero); accumulates into the bound gradient
+    arena.  Stages 0..3 = gradient buckets (torsion head + block 3 | block 2 | block 1 | block 0 + embedders)."""
+    from ._lib import TrainGrads
+    dev = self.device
+    conv = lambda k, dt: None if dout.get(k) is None else dout[k].to(dev, dt).contiguous()
+    keep = [conv("rot_score", torch.float64), conv("trans_score", torch.float64), conv("rigids", torch.float32), conv("atom37", torch.float32),
+            conv("atom14", torch.float32), conv("psi", torch.float32)]
+    g = TrainGrads(*[_ptr(t) for t in keep])
+    st = torch.cuda.current_stream(dev)
+    check(self.lib.fd_train_backward(self._h, C.byref(g), int(stage_first), int(stage_last), C.c_void_p(st.cuda_stream)))
+    self._train_dout_keep = keep
+
+
+def _loss_backward(self, model_out: dict, batch: dict, exp_conf: Optional[dict] = None, diffuse_trans: bool = True, diffuse_rot: bool = True) -> dict:
+    """d total_loss / d model outputs of the reference's loss_fn, on the device (fd_loss_backward)."""
+    from ._lib import LossCfg, LossIn, TrainGradsOut
+    dev = self.device
+    conf = dict(DEFAULT_EXP_CONF, **({} if exp_conf is None else dict(exp_conf)))
+    dv = lambda x, dtype: torch.as_tensor(x).to(device=dev, dtype=dtype).contiguous()
+    res_mask = dv(batch["res_mask"], torch.float32)
+    B, N = res_mask.shape
+    keep = dict(
+        pred_rot_score=dv(model_out["rot_score"], torch.float64), pred_trans_score=dv(model_out["trans_score"], torch.float64),
+        pred_rigids=dv(model_out["rigids"], torch.float32), pred_atom37=dv(model_out["atom37"], torch.float32),
+        gt_rot_score=dv(batch["rot_score"], torch.float64), gt_trans_score=dv(batch["trans_score"], torch.float64),
+        rot_score_scaling=dv(batch["rot_score_scaling"], torch.float64), trans_score_scaling=dv(batch["trans_score_scaling"], torch.float64),
+        rigids_0=dv(batch["rigids_0"], torch.float64), t=dv(batch["t"], torch.float64), res_mask=res_mask,
+        fixed_mask=dv(batch["fixed_mask"], torch.float32), gt_psi=dv(torch.as_tensor(batch["torsion_angles_sin_cos"])[..., 2, :], torch.float32))
+    lin = LossIn(*[_ptr(keep[k]) for k, _ in LossIn._fields_])
+    cfg = LossCfg(*[float(conf[k]) for k, ty in LossCfg._fields_ if ty is C.c_double], int(bool(conf["separate_rot_loss"])),
+                  int(bool(diffuse_trans)), int(bool(diffuse_rot)))
+    out = {"rot_score": torch.empty(B, N, 3, device=dev, dtype=torch.float64), "trans_score": torch.empty(B, N, 3, device=dev, dtype=torch.float64),
+           "rigids": torch.empty(B, N, 7, device=dev, dtype=torch.float32), "atom37": torch.empty(B, N, 37, 3, device=dev, dtype=torch.float32)}
+    go = TrainGradsOut(*[_ptr(out[k]) for k in ("rot_score", "trans_score", "rigids", "atom37")])
+    st = torch.cuda.current_stream(dev)
+    check(self.lib.fd_loss_backward(self._h, B, N, C.byref(lin), C.byref(cfg), C.byref(go), C.c_void_p(st.cuda_stream)))
+    return out
+
+
+def _adam_step(self, params: torch.Tensor, grads: torch.Tensor, exp_avg: torch.Tensor, exp_avg_sq: torch.Tensor, step: int, lr: float = 1e-4,
+               betas=(0.9, 0.999), eps: float = 1e-8, grad_scale: float = 1.0):
+    st = torch.cuda.current_stream(self.device)
+    check(self.lib.fd_adam_step(self._h, _ptr(params), _ptr(grads), _ptr(exp_avg), _ptr(exp_avg_sq), params.numel(), float(lr), float(betas[0]),
+                                float(betas[1]), float(eps), int(step), float(grad_scale), C.c_void_p(st.cuda_stream)))
+
+
+FrameDiffEngine.train_bind = _train_bind
+FrameDiffEngine.train_forward = _train_forward
+FrameDiffEngine.train_backward = _train_backward
+FrameDiffEngine.loss_backward = _loss_backward
+FrameDiffEngine.adam_step = _adam_step
