@@ -41,6 +41,9 @@ def parse():
     p.add_argument("--precision", default=None, choices=[None, "fp32", "bf16x3", "bf16"])
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--cpu-steps", type=int, default=2, help="denoise steps of the bounded CPU sample")
+    p.add_argument("--mode", default="sample", choices=["sample", "train"],
+                   help="sample (default, the headline metric) | train: one optimiser step (fwd + DSM loss + bwd + all-reduce + Adam), BASELINE config 4")
+    p.add_argument("--lr", type=float, default=1e-4)
     return p.parse_args()
 
 
@@ -163,10 +166,131 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+TRAIN_METRIC = "training examples/sec (fwd + DSM loss + bwd + gradient all-reduce + Adam, N=256)"
+
+
+def train_flops(B, N):
+    """Executed FLOPs of one training step: forward (separable EdgeTransition / lookup layer-0 algebra, fd_forward_flops executed) +
+    backward = 2x forward (dgrad + wgrad of every GEMM); loss and Adam are O(N^2) / O(params) and ignored."""
+    n2 = float(N) * N
+    fwd = (2248960.0 - 3 * (688128.0 - 524288.0)) * n2 + 32421376.0 * N       # dense layer-0 edge embedder in training (no table lookup)
+    return 3.0 * fwd * B
+
+
+def cpu_train_baseline(N, state):
+    """The reference's training step on the host: autograd through the oracle port (forward + loss_fn + backward) + torch Adam, 1 example."""
+    import torch
+    from oracle import framediff_oracle as fo
+    torch.set_num_threads(min(os.cpu_count() or 1, 32))
+    w = {k: v.clone().requires_grad_(True) for k, v in fo.as_torch_weights(state).items()}
+    opt = torch.optim.Adam(list(w.values()), lr=1e-4)
+    np.random.seed(3)
+    r0 = fo.sample_ref(N).numpy().astype(np.float64); r0[:, 4:] *= 0.35
+    fm = fo.forward_marginal(torch.tensor(r0), 0.5)
+    tors = np.random.randn(N, 7, 2); tors /= np.linalg.norm(tors, axis=-1, keepdims=True)
+    batch = {"rigids_0": torch.tensor(r0)[None], "rigids_t": fm["rigids_t"][None].float(), "rot_score": torch.tensor(fm["rot_score"])[None],
+             "trans_score": torch.tensor(fm["trans_score"])[None], "rot_score_scaling": torch.tensor([fm["rot_score_scaling"]]),
+             "trans_score_scaling": torch.tensor([fm["trans_score_scaling"]]), "res_mask": torch.ones(1, N, dtype=torch.float64),
+             "fixed_mask": torch.zeros(1, N, dtype=torch.float64), "seq_idx": torch.arange(1, N + 1)[None],
+             "torsion_angles_sin_cos": torch.tensor(tors)[None], "sc_ca_t": torch.zeros(1, N, 3, dtype=torch.float64), "t": torch.tensor([0.5], dtype=torch.float64)}
+    t0 = time.perf_counter()
+    out = fo.score_network_forward(w, batch, float_mask_quirk=True)
+    loss = fo.loss_terms(out, batch)["total_loss"]
+    opt.zero_grad(); loss.backward(); opt.step()
+    dt = time.perf_counter() - t0
+    return {"value": 1.0 / dt, "unit": "examples/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"1 example x N={N}: forward + loss_fn + backward (torch autograd through the oracle port) + Adam in {dt:.2f} s",
+            "seconds_measured": dt}
+
+
+def run_train(args):
+    """--mode train: BASELINE config 4 (B=8 examples/GPU x N=256, DDP over the ranks)."""
+    import torch
+    import torch.distributed as dist
+    from se3_diffusion_b200 import FrameDiffEngine
+    from se3_diffusion_b200.parallel import TrainStep
+    from se3_diffusion_b200.synthetic import training_batch
+    world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    B, N = args.batch or 8, args.nres
+    eng = FrameDiffEngine(local, "fp32")
+    state = synthetic_state()
+    ts = TrainStep(eng, state, lr=args.lr)
+    ts.broadcast_parameters()
+    batch = training_batch(eng, B, N, seed=1 + rank)
+    FE = ("rigids_t", "res_mask", "fixed_mask", "seq_idx", "t", "sc_ca_t", "torsion_angles_sin_cos")
+    dev_batch = {k: v.to(dev) for k, v in batch.items()}
+    pin_batch = {k: v.pin_memory() for k, v in batch.items()}
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def dev_step():
+        return ts({k: dev_batch[k] for k in FE}, dev_batch)
+
+    def e2e_step():
+        hb = {k: v.to(dev, non_blocking=True) for k, v in pin_batch.items()}      # H2D of the whole batch from pinned memory
+        loss = ts({k: hb[k] for k in FE}, hb)
+        return float(loss.item())                                                  # D2H of the step's result
+
+    for _ in range(args.warmup):
+        dev_step()
+    barrier()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    l0 = eng.lib.fd_num_params()   # noqa (keeps the lib symbol table warm)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    dev_ms = e2e_ms = 0.0
+    exposed = 0.0
+    launches0 = None
+    losses = []
+    for i in range(args.steps):          # the two legs interleaved step by step (same clock / power state)
+        barrier(); ev[0].record(); dev_step(); ev[1].record(); barrier()
+        dev_ms += ev[0].elapsed_time(ev[1]); exposed += ts.exposed_comm_ms()
+        barrier(); t0 = time.perf_counter(); losses.append(e2e_step()); barrier()
+        e2e_ms += (time.perf_counter() - t0) * 1e3
+    t = torch.tensor([dev_ms, e2e_ms, exposed], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_s, e2e_s, exposed_ms = float(t[0]) / 1e3 / args.steps, float(t[1]) / 1e3 / args.steps, float(t[2]) / args.steps
+    clk = clocks.stop() if rank == 0 else None
+    if rank == 0:
+        pk = peaks()
+        fl = train_flops(B, N)
+        ach = fl / dev_s / 1e12
+        h2d = int(sum(v.numel() * v.element_size() for v in batch.values()))
+        cb = None if args.no_cpu_baseline else cpu_train_baseline(N, state)
+        line = {"metric": TRAIN_METRIC, "value": world * B / dev_s, "unit": "examples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": dev_s * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic (random-init weights; CA random-walk backbones noised with forward_marginal, SURVEY §8(d))",
+                "config": {"workload": f"train step, {B} examples/GPU x N={N} (BASELINE config 4 per-GPU shard), DDP over {world} GPU(s)",
+                           "batch_per_gpu": B, "global_batch": world * B, "nres": N, "parallelism": f"dp{world}", "optimizer": "Adam",
+                           "l2": "not flushed: every layer streams the %.0f MB fp32 edge tensor (> 126 MB L2)" % (B * N * N * 128 * 4 / 1e6)},
+                "e2e": {"value": world * B / e2e_s, "unit": "examples/s", "ms_per_step": e2e_s * 1e3, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8},
+                "comm_exposed_ms_per_step": exposed_ms, "allreduce_bytes_per_step": int(ts.grads.numel() * 4) if world > 1 else 0,
+                "final_loss": losses[-1] if losses else None, "clocks": clk,
+                "roofline": {"bound": "tensor", "kernel": "whole training step (fp32 CUDA-core GEMMs in this round: forward, dgrad, wgrad)",
+                             "achieved": ach, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": ach / pk["bf16_tflops_sustained"],
+                             "peak_source": pk["source"], "traffic": None, "executed_flops_per_step": fl},
+                "cpu_baseline": cb}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     args = parse()
     if args.impl == "reference":
         return run_reference(args)
+    if args.mode == "train":
+        return run_train(args)
     import torch
     import torch.distributed as dist
     from se3_diffusion_b200 import FrameDiffEngine

@@ -444,6 +444,8 @@ def _train_forward(self, feats: Dict[str, torch.Tensor]) -> Dict[str, torch.Tens
     self._train_keep = keep            # inputs must outlive the backward
     if t_is_f32:
         out["trans_score"] = out["trans_score"].to(torch.float32)
+    if tors is not None and torch.as_tensor(tors).dtype == torch.float64:
+        out["psi"] = out["psi"].to(torch.float64)
     return out
 
 

@@ -6,8 +6,13 @@
 `forward(input_feats) -> dict` has the reference's keys, shapes and dtypes (model/score_network.py:170-215) but runs the
 whole network in libframediff_b200.so.  The nn.Module is only the parameter container: no torch op takes part in the forward.
 
-Training (autograd through the CUDA path) is not built yet (SURVEY §8 rows a27/a28 — the next milestone): calling forward
-with gradients enabled on trainable parameters raises instead of silently returning graph-less tensors.
+Training: with gradients enabled on trainable parameters, forward runs the training-mode CUDA forward (fd_train_forward: autograd
+semantics of the sequence attention, activations kept on a tape) and returns tensors attached to a torch.autograd.Function whose
+backward is the hand-written CUDA backward (fd_train_backward) — so the reference's `loss_fn(...)`, `loss.backward()`,
+`torch.optim.Adam` and DDP wrappers (experiments/train_se3_diffusion.py:139-141,268-286,320-326) work unchanged.  The parameters
+are views into one flat fp32 arena in state_dict order (the layout the kernels read and the gradient arena mirrors); the 10
+parameters the reference never uses (linear_rbf, torsion_pred.linear_3) are not inputs of the Function and keep grad None, exactly
+like under the reference's autograd (DDP find_unused_parameters=True).
 """
 from __future__ import annotations
 
@@ -16,7 +21,34 @@ import math
 import torch
 from torch import nn
 
-from .engine import FrameDiffEngine
+from .engine import FrameDiffEngine, arena_layout
+
+_OUT_KEYS = ("psi", "rot_score", "trans_score", "rigids", "atom37", "atom14")
+
+
+def _is_unused(name: str) -> bool:
+    return ".linear_rbf." in name or name.startswith("score_model.torsion_pred.linear_3.")
+
+
+class _ScoreNetworkFn(torch.autograd.Function):
+    """ScoreNetwork.forward / backward on the CUDA training path.  Inputs after `net` and `feats` are the USED parameters (so that autograd
+    — and DDP's reducer hooks — see them); outputs are the reference's six tensors."""
+
+    @staticmethod
+    def forward(ctx, net, feats, *params):
+        eng = net._training_engine()
+        out = eng.train_forward(feats)
+        ctx.net = net
+        ctx.dtypes = {k: out[k].dtype for k in _OUT_KEYS}
+        return tuple(out[k] for k in _OUT_KEYS)
+
+    @staticmethod
+    def backward(ctx, *douts):
+        net = ctx.net
+        eng = net._training_engine()
+        net._grad_flat.zero_()
+        eng.train_backward({k: d for k, d in zip(_OUT_KEYS, douts)})
+        return (None, None) + tuple(net._used_grad_views)
 
 _TRUNC_STD = 0.87962566103423978   # std of a standard normal truncated to [-2, 2] (scipy.stats.truncnorm.std(-2, 2))
 
@@ -145,6 +177,8 @@ class ScoreNetwork(nn.Module):
         self.precision = precision
         self._engine_obj = None
         self._loaded_version = None
+        self._param_flat = None        # training: one flat fp32 arena the parameters are views of (engine.arena_layout order)
+        self._grad_flat = None
 
     # ---- engine management ---------------------------------------------------------------------------------------------
     def _weights_key(self):
@@ -179,14 +213,57 @@ class ScoreNetwork(nn.Module):
             self._loaded_version = ver
         return self._engine_obj
 
+    # ---- training path -------------------------------------------------------------------------------------------------------
+    def _flatten_parameters(self, dev):
+        """(Re)points every parameter at its slice of one flat arena (values preserved).  Cheap check on every training forward, so
+        `.to()`, `load_state_dict` into fresh tensors or external re-allocations are picked up."""
+        lay, total = arena_layout()
+        named = dict(self.named_parameters())
+        flat = self._param_flat
+        ok = flat is not None and flat.device == dev and all(
+            named[n].data_ptr() == flat.data_ptr() + 4 * off and named[n].is_contiguous() for n, _, off in lay)
+        if ok:
+            return
+        flat = torch.zeros(total, dtype=torch.float32, device=dev)
+        with torch.no_grad():
+            for n, shape, off in lay:
+                view = flat[off:off + named[n].numel()].view(shape)
+                view.copy_(named[n].detach().to(dev, torch.float32))
+                named[n].data = view
+        self._param_flat = flat
+        self._grad_flat = torch.zeros_like(flat)
+        gv = {n: self._grad_flat[off:off + named[n].numel()].view(shape) for n, shape, off in lay}
+        self._used_names = [n for n, _, _ in lay if not _is_unused(n)]
+        self._used_params = [named[n] for n in self._used_names]
+        self._used_grad_views = [gv[n] for n in self._used_names]
+        self._loaded_version = None
+
+    def _training_engine(self) -> FrameDiffEngine:
+        dev = self._param_flat.device
+        if self._engine_obj is None or self._engine_obj.device != dev:
+            self._engine_obj = FrameDiffEngine(dev, self.precision)
+            self._loaded_version = None
+            if hasattr(self.diffuser, "bind_engine"):
+                self.diffuser.bind_engine(self._engine_obj)
+        arenas = getattr(self._engine_obj, "_train_arenas", None)
+        if arenas is None or arenas[0] is not self._param_flat:
+            self._engine_obj.train_bind(self._param_flat, self._grad_flat)
+        return self._engine_obj
+
     def forward(self, input_feats):
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()) and self.training:
-            raise NotImplementedError(
-                "ScoreNetwork (B200): the backward pass / training step is not implemented yet (SURVEY.md §8 rows a27-a28); "
-                "run under torch.no_grad() / .eval() for sampling")
         dev = input_feats["rigids_t"].device
         if dev.type != "cuda":
             raise RuntimeError("ScoreNetwork (B200) has no CPU path: move the model and its inputs to a CUDA device")
+        needs_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+        if needs_grad or self.training:
+            # torch's TransformerEncoder leaves its fused inference path whenever the module is in train() mode or autograd records; the
+            # training-mode CUDA forward has those semantics (float key-padding mask added to the logits, SURVEY Appendix C.2)
+            self._flatten_parameters(torch.device(dev))
+            if needs_grad:
+                outs = _ScoreNetworkFn.apply(self, input_feats, *self._used_params)
+                return dict(zip(_OUT_KEYS, outs))
+            out = self._training_engine().train_forward(input_feats)
+            return {k: out[k] for k in _OUT_KEYS}
         eng = self.engine(dev)
         out = eng.forward(input_feats)
-        return {k: out[k] for k in ("psi", "rot_score", "trans_score", "rigids", "atom37", "atom14")}
+        return {k: out[k] for k in _OUT_KEYS}

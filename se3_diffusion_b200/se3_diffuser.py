@@ -185,6 +185,10 @@ class SE3Diffuser:
         grid = self._so3_diffuser.sigma(np.linspace(0.0, 1.0, 1000))
         sig_q = float(grid[np.digitize(sig, grid) - 1])
         rot_score = self._engine().igso3_score(rotvec, torch.full(rotvec.shape[:-1], sig_q, dtype=torch.float64)).cpu().numpy()
+        if rot_score.ndim == 2:
+            # the reference's SO3Diffuser.score calls torch_score(vec, tensor(t)[None]): its [1,1] sigma broadcasts against the [N] angles,
+            # so an [N,7] input comes back as [1,N,3] (so3_diffuser.py:268-272) — kept
+            rot_score = rot_score[None]
         trans_score = self.calc_trans_score(rt[..., 4:].cpu().numpy(), r0[..., 4:].cpu().numpy(), t, scale=False)
         return trans_score, rot_score
 

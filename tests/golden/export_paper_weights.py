@@ -15,7 +15,7 @@ import ref_harness as rh  # noqa: E402
 if __name__ == "__main__":
     root = os.path.dirname(os.path.dirname(HERE))
     os.makedirs(os.path.join(root, "weights"), exist_ok=True)
-    for name in ("paper_weights", "best_weights"):
+    for name in (("paper_weights", "best_weights") if "--all" in sys.argv else ("paper_weights",)):   # 70 MB each: only what the tests use
         sd = rh.load_reference_checkpoint(name + ".pth")
         out = os.path.join(root, "weights", name + ".npz")
         np.savez(out, **{k: v.numpy() for k, v in sd.items()})

@@ -434,6 +434,8 @@ def test_diffuser_api_score_on_gpu(eng):
     dif.bind_engine(eng)
     ts, rs = dif.score(torch.tensor(g["rigids_0"]), torch.tensor(g["rigids_1"]), float(g["score_t"]))
     assert_close(ts, g["score_trans"], 1e-6, atol=1e-9, name="score trans")
+    assert np.asarray(rs).shape == g["score_rot"].shape          # incl. the reference's leading broadcast dimension
+    rs, g = np.asarray(rs).reshape(-1, 3), dict(g, score_rot=g["score_rot"].reshape(-1, 3))
     sig = fo.discrete_sigma()[fo.so3_t_to_idx(float(g["score_t"]))]
     om = np.linalg.norm(fo._rotvec_from_quat7(torch.tensor(g["rigids_1"]))[1], axis=-1)
     ok = om <= 3.5 * sig
@@ -613,9 +615,13 @@ def test_score_network_module_forward_matches_reference_golden():
     assert set(out) == {"psi", "rot_score", "trans_score", "rigids", "atom37", "atom14"}
     ref = {k[4:]: v for k, v in g.items() if k.startswith("out_")}
     _check_forward(out, ref, g["in_t"], g["in_rigids_t"])
+    # train() mode without autograd (the self-conditioning forward inside loss_fn): torch's TransformerEncoder is off its fused path there,
+    # i.e. the float key-padding mask is added to the logits — the training-mode CUDA forward; equals the oracle with float_mask_quirk
     net.train()
-    with pytest.raises(NotImplementedError):
-        net(f)                                               # training path not built yet: loud, not silent
+    with torch.no_grad():
+        out_t = net(f)
+        ref_t = fo.score_network_forward(fo.as_torch_weights(synthetic_state(0)), feats_from_golden(g), float_mask_quirk=True)
+    _check_forward(out_t, {k: v.numpy() for k, v in ref_t.items()}, g["in_t"], g["in_rigids_t"])
 
 
 def test_inference_fn_numpy_noise_matches_reference_golden(eng):

