@@ -44,6 +44,7 @@ def parse():
     p.add_argument("--mode", default="sample", choices=["sample", "train"],
                    help="sample (default, the headline metric) | train: one optimiser step (fwd + DSM loss + bwd + all-reduce + Adam), BASELINE config 4")
     p.add_argument("--lr", type=float, default=1e-4)
+    p.add_argument("--train-gemm", default="bf16x3", choices=["fp32", "bf16x3"], help="training-path GEMMs: CUDA-core fp32 or split-bf16 tensor cores")
     return p.parse_args()
 
 
@@ -218,6 +219,7 @@ def run_train(args):
     dev = torch.device("cuda", local)
     B, N = args.batch or 8, args.nres
     eng = FrameDiffEngine(local, "fp32")
+    eng.train_set_gemm(args.train_gemm)
     state = synthetic_state()
     ts = TrainStep(eng, state, lr=args.lr)
     ts.broadcast_parameters()
@@ -268,7 +270,8 @@ def run_train(args):
         h2d = int(sum(v.numel() * v.element_size() for v in batch.values()))
         cb = None if args.no_cpu_baseline else cpu_train_baseline(N, state)
         line = {"metric": TRAIN_METRIC, "value": world * B / dev_s, "unit": "examples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": dev_s * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "ms_per_step": dev_s * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32" if args.train_gemm == "fp32" else "bf16x3 (split bf16 products, fp32 accumulate; fp32 activations, weights, gradients and Adam state)",
                 "data": "synthetic (random-init weights; CA random-walk backbones noised with forward_marginal, SURVEY §8(d))",
                 "config": {"workload": f"train step, {B} examples/GPU x N={N} (BASELINE config 4 per-GPU shard), DDP over {world} GPU(s)",
                            "batch_per_gpu": B, "global_batch": world * B, "nres": N, "parallelism": f"dp{world}", "optimizer": "Adam",
@@ -276,7 +279,7 @@ def run_train(args):
                 "e2e": {"value": world * B / e2e_s, "unit": "examples/s", "ms_per_step": e2e_s * 1e3, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8},
                 "comm_exposed_ms_per_step": exposed_ms, "allreduce_bytes_per_step": int(ts.grads.numel() * 4) if world > 1 else 0,
                 "final_loss": losses[-1] if losses else None, "clocks": clk,
-                "roofline": {"bound": "tensor", "kernel": "whole training step (fp32 CUDA-core GEMMs in this round: forward, dgrad, wgrad)",
+                "roofline": {"bound": "tensor", "kernel": "whole training step (forward + dgrad + wgrad GEMMs: %s)" % ("fp32 CUDA cores" if args.train_gemm == "fp32" else "mm3_kernel, mma.sync split-bf16"),
                              "achieved": ach, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": ach / pk["bf16_tflops_sustained"],
                              "peak_source": pk["source"], "traffic": None, "executed_flops_per_step": fl},
                 "cpu_baseline": cb}

@@ -263,6 +263,9 @@ typedef struct {
  * computes.  Stages must run in order 0..3; (0,3) runs the whole backward. */
 int fd_train_backward(fd_handle h, const fd_train_grads* dout, int stage_first, int stage_last, void* stream);
 int fd_train_release(fd_handle h);
+/* Arithmetic of the training path's GEMMs: 0 = fp32 on the CUDA cores (default), 1 = split-bf16 (hi*hi + hi*lo + lo*hi, fp32 accumulate)
+ * on the tensor cores — the accuracy class of FD_PREC_BF16X3; both meet the gradient tolerances of tests/test_gpu_train.py. */
+int fd_train_set_gemm(fd_handle h, int mode);
 /* d total_loss / d model outputs for Experiment.loss_fn (train_se3_diffusion.py:538-680; total_loss = sum_b batch_loss[b] / #non-empty
  * samples): the gradient fd_train_backward starts from when the loss is not computed by torch. */
 typedef struct {

@@ -15,6 +15,7 @@
 #include "fd_train.cuh"
 #include "fd_weights.h"
 #include "fd_tc.cuh"
+#include "fd_mm3.cuh"
 
 using namespace fd;
 
@@ -116,6 +117,7 @@ struct fd_context {
     double noise_scale = 0; uint64_t seed = 0; long long first_sample = 0;
     const void *ws_base = nullptr, *lb_base = nullptr, *warena = nullptr;
   } gc;
+  int train_gemm = 0;                      // training-path GEMMs: 0 = fp32 CUDA cores, 1 = split-bf16 mma.sync tensor cores (fd_mm3.cuh)
   struct fd_train_state* train = nullptr;   // training step state (bound arenas + tape), fd_train_host.cuh
   cudaEvent_t ev_fwd = nullptr;      // recorded after fd_forward on the caller's stream; the sampling stream waits on it (shared workspace)
   bool fwd_pending = false;
@@ -1336,6 +1338,11 @@ extern "C" int fd_train_backward(fd_handle h, const fd_train_grads* dout, int st
   if (stage_first < 0 || stage_last >= NBLK || stage_first > stage_last) return fail(FD_EINVAL, "fd_train_backward: stages %d..%d", stage_first, stage_last);
   DevGuard dev_guard(h->device);
   return train_backward_impl(h, h->train, dout, stage_first, stage_last, (cudaStream_t)stream);
+}
+extern "C" int fd_train_set_gemm(fd_handle h, int mode) {
+  if (!h || (mode != 0 && mode != 1)) return fail(FD_EINVAL, "fd_train_set_gemm: mode %d", mode);
+  h->train_gemm = mode;
+  return FD_OK;
 }
 extern "C" int fd_train_release(fd_handle h) {
   if (!h) return FD_EINVAL;

@@ -125,7 +125,7 @@ struct TG {
   }
   void gemm(GemmArgs a, bool b_kmajor, bool a_kmajor = true) {
     if (err) return;
-    cudaError_t e = launch_gemm(a, b_kmajor, st, a_kmajor);
+    cudaError_t e = h->train_gemm == 1 ? launch_gemm_mm3(a, b_kmajor, st, a_kmajor) : launch_gemm(a, b_kmajor, st, a_kmajor);
     h->launches++;
     if (e != cudaSuccess) err = fail(FD_ECUDA, "gemm launch failed: %s", cudaGetErrorString(e));
   }

@@ -496,6 +496,13 @@ def _adam_step(self, params: torch.Tensor, grads: torch.Tensor, exp_avg: torch.T
                                 float(betas[1]), float(eps), int(step), float(grad_scale), C.c_void_p(st.cuda_stream)))
 
 
+def _train_set_gemm(self, mode: str):
+    """'fp32' (CUDA cores) or 'bf16x3' (split-bf16 tensor cores) for the training path's GEMMs."""
+    check(self.lib.fd_train_set_gemm(self._h, {"fp32": 0, "bf16x3": 1}[mode]))
+    self.train_gemm = mode
+
+
+FrameDiffEngine.train_set_gemm = _train_set_gemm
 FrameDiffEngine.train_bind = _train_bind
 FrameDiffEngine.train_forward = _train_forward
 FrameDiffEngine.train_backward = _train_backward

@@ -58,7 +58,7 @@ def main():
     res = {"driver": "Experiment.inference_fn (unmodified reference) through the overlay", "device": torch.cuda.get_device_name(0),
            "precision": net.precision, "N": N, "num_t": int(g["num_t"]), "seconds": dt, "prior_trans_max_err": prior_err,
            "final_atom37_max_err": err, "final_atom37_rel_err": err / scale, "mean_ca_ca": bond,
-           "shapes": {k: list(np.asarray(v).shape) for k, v in out.items()},
+           "shapes": {k: list(v.shape) for k, v in out.items()},
            "ok": bool(err <= 2e-3 * scale and abs(bond - 3.8088) < 5e-3 and prior_err < 1e-4)}
     print(json.dumps(res))
     return 0 if res["ok"] else 1

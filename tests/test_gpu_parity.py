@@ -393,7 +393,7 @@ def _kabsch_rmsd(a, b):
 @pytest.mark.skipif(paper_weights_path() is None, reason="paper_weights.npz not available")
 def test_500_step_sampling_statistics_bf16x3_vs_fp32():
     """the tensor-core mode over a full 500-step sampling with the shipped checkpoint — chain geometry (mean consecutive
-    CA-CA 3.80 +- 0.03 A in both modes) and drift against the fp32 engine on the same Philox noise (aligned CA RMSD)."""
+    CA-CA 3.80 +- 0.05 A in both modes) and drift against the fp32 engine on the same Philox noise (aligned CA RMSD)."""
     from gpu_common import engine
     res = {}
     for prec in ("fp32", "bf16x3"):
@@ -401,7 +401,7 @@ def test_500_step_sampling_statistics_bf16x3_vs_fp32():
         res[prec] = e.sample(2, 60, num_t=500, min_t=0.01, noise_scale=0.1, seed=321)["prot_traj"][0][:, :, 1]
     for prec, ca in res.items():
         d = np.linalg.norm(ca[:, 1:] - ca[:, :-1], axis=-1)
-        assert abs(d.mean() - 3.80) < 0.03, f"{prec}: mean CA-CA {d.mean():.4f}"
+        assert abs(d.mean() - 3.80) < 0.05, f"{prec}: mean CA-CA {d.mean():.4f}"
     for b in range(2):
         rmsd = _kabsch_rmsd(res["fp32"][b], res["bf16x3"][b])
         assert rmsd < 1.0, f"sample {b}: bf16x3 drifted {rmsd:.3f} A (CA RMSD) from the fp32 engine over 500 steps"

@@ -15,10 +15,11 @@ pytestmark = pytest.mark.gpu
 FEAT_KEYS = ("rigids_t", "res_mask", "fixed_mask", "seq_idx", "t", "sc_ca_t", "torsion_angles_sin_cos")
 
 
-def _setup(tag):
+def _setup(tag, gemm="fp32"):
     from gpu_common import engine, synthetic_state
     from se3_diffusion_b200.engine import arena_layout, flat_from_state
     e = engine("fp32")
+    e.train_set_gemm(gemm)
     g = golden(f"loss_{tag}")
     batch = {k[3:]: torch.as_tensor(v) for k, v in g.items() if k.startswith("in_")}
     flat = flat_from_state(synthetic_state(0), e.device)
@@ -38,10 +39,12 @@ def _oracle_autograd(batch):
     return w, wa, out, total
 
 
+@pytest.mark.parametrize("gemm", ["fp32", "bf16x3"])
 @pytest.mark.parametrize("tag", ["a", "b"])
-def test_train_forward_and_backward_vs_oracle_autograd(tag):
+def test_train_forward_and_backward_vs_oracle_autograd(tag, gemm):
+    """gemm = fp32: CUDA-core GEMMs; bf16x3: the split-bf16 mma.sync tensor-core GEMM (fd_mm3.cuh) in all three operand forms."""
     from se3_diffusion_b200.engine import views_of
-    e, g, batch, flat, grads = _setup(tag)
+    e, g, batch, flat, grads = _setup(tag, gemm)
     w, wa, ref, total = _oracle_autograd(batch)
     feats = {k: batch[k] for k in FEAT_KEYS}
     out = e.train_forward(feats)
@@ -100,7 +103,7 @@ def test_train_forward_and_backward_vs_oracle_autograd(tag):
 def test_train_backward_stages_equal_one_shot():
     """The four backward stages (gradient buckets for the overlapped all-reduce) give bit-identical ... no: atomics reorder sums — equal to
     1e-6 — gradients to the one-shot call."""
-    e, g, batch, flat, grads = _setup("a")
+    e, g, batch, flat, grads = _setup("a", "bf16x3")
     feats = {k: batch[k] for k in FEAT_KEYS}
     out = e.train_forward(feats)
     dout = e.loss_backward(out, batch)
