@@ -71,11 +71,14 @@ def test_train_forward_and_backward_vs_oracle_autograd(tag, gemm):
             taps = {}
             mb.train_backward(w, tape, dout, taps=taps)
         B, N = batch["res_mask"].shape
+        # intermediate gradients are sums of much larger terms that cancel (the edge gradient by ~100x): the split-bf16 GEMMs' 1e-5 element
+        # error shows up magnified there; the parameter gradients below are the acceptance criterion
+        tap_tol = 5e-4 if gemm == "fp32" else 1e-2
         for b in (3, 2, 1, 0):
-            assert_close(e.debug_fetch(f"dquat_{b}", (B, N, 4)), taps[f"dquat_{b}"].numpy(), 0, norm_rel=5e-4, name=f"dquat_{b}")
-            assert_close(e.debug_fetch(f"dtrans_{b}", (B, N, 3)), taps[f"dtrans_{b}"].numpy(), 0, norm_rel=5e-4, name=f"dtrans_{b}")
-            assert_close(e.debug_fetch(f"dnode_{b}", (B, N, 256)), taps[f"dnode_{b}"].numpy(), 0, norm_rel=5e-4, name=f"dnode_{b}")
-            assert_close(e.debug_fetch(f"dz_{b}", (B, N, N, 128)), taps[f"dz_{b}"].numpy(), 0, norm_rel=5e-4, name=f"dz_{b}")
+            assert_close(e.debug_fetch(f"dquat_{b}", (B, N, 4)), taps[f"dquat_{b}"].numpy(), 0, norm_rel=tap_tol, name=f"dquat_{b}")
+            assert_close(e.debug_fetch(f"dtrans_{b}", (B, N, 3)), taps[f"dtrans_{b}"].numpy(), 0, norm_rel=tap_tol, name=f"dtrans_{b}")
+            assert_close(e.debug_fetch(f"dnode_{b}", (B, N, 256)), taps[f"dnode_{b}"].numpy(), 0, norm_rel=tap_tol, name=f"dnode_{b}")
+            assert_close(e.debug_fetch(f"dz_{b}", (B, N, N, 128)), taps[f"dz_{b}"].numpy(), 0, norm_rel=tap_tol, name=f"dz_{b}")
     finally:
         e.set_debug(False)
     gv = views_of(grads)
@@ -88,16 +91,18 @@ def test_train_forward_and_backward_vs_oracle_autograd(tag, gemm):
             continue
         n_used += 1
         tol = 1e-6 if n.endswith("linear_b.bias") else 0.0
-        assert_close(got, wa[n].grad.numpy(), 0, norm_rel=5e-4, atol=tol, name=n)
+        # bf16x3: every product carries ~2^-16 relative error (fp32: 2^-24); a weight gradient is a sum over up to B*N^2 rows of signed terms that
+        # largely cancel, so relative to the result the error is ~1e-3 — the documented accuracy class of the tensor-core training mode
+        assert_close(got, wa[n].grad.numpy(), 0, norm_rel=5e-4 if gemm == "fp32" else 3e-3, atol=tol, name=n)
     assert n_used == 272
     # ---- and the reference's own numbers (KAT): 272 gradient norms + three full tensors ----
     for n, rn in zip(names, norms):
         if rn >= 0:
             gn = float(np.linalg.norm(gv[n].double().cpu().numpy()))
-            assert abs(gn - rn) <= 5e-4 * rn + 1e-6, (n, gn, rn)
+            assert abs(gn - rn) <= (5e-4 if gemm == "fp32" else 2e-3) * rn + 1e-6, (n, gn, rn)
     for k in g:
         if k.startswith("grad::"):
-            assert_close(gv[k[6:]].cpu().numpy(), g[k], 0, norm_rel=5e-4, name=k)
+            assert_close(gv[k[6:]].cpu().numpy(), g[k], 0, norm_rel=5e-4 if gemm == "fp32" else 3e-3, name=k)
 
 
 def test_train_backward_stages_equal_one_shot():

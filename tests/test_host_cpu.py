@@ -170,3 +170,62 @@ def test_product_code_never_imports_the_oracle():
     for pos in legs:        # every oracle import sits inside the CPU-baseline or the reference-arm function
         fn_start = max(m.start() for m in re.finditer(r"^def \w+", src[:pos], re.M))
         assert src[fn_start:fn_start + 40].startswith(("def cpu_baseline", "def run_reference")), src[fn_start:fn_start + 60]
+
+
+def test_grad_buckets_partition_the_arena():
+    """The four backward stages' gradient buckets are contiguous, disjoint, cover the whole flat arena and follow the order the stages
+    finish in (block 3 + torsion head first, embedders + block 0 last)."""
+    from se3_diffusion_b200.engine import arena_layout
+    from se3_diffusion_b200.parallel import grad_buckets
+    lay, total = arena_layout()
+    bk = grad_buckets()
+    assert len(bk) == 4 and bk[0][1] == total and bk[3][0] == 0
+    assert all(bk[i][0] == bk[i + 1][1] for i in range(3)) and all(lo < hi for lo, hi in bk)
+    where = {n: next(i for i, (lo, hi) in enumerate(bk) if lo <= off < hi) for n, _, off in lay}
+    assert where["score_model.torsion_pred.linear_1.weight"] == 0 and where["score_model.trunk.ipa_3.linear_q.weight"] == 0
+    assert where["score_model.trunk.edge_transition_2.trunk.0.weight"] == 1 and where["score_model.trunk.ipa_1.linear_q.weight"] == 2
+    assert where["embedding_layer.edge_embedder.0.weight"] == 3 and where["score_model.trunk.bb_update_0.linear.weight"] == 3
+    assert sum(int(np.prod(s)) for _, s, _ in lay) == 17446190          # SURVEY §8(e): 17,446,190 fp32 parameters
+
+
+def test_train_step_allreduce_logic_gloo():
+    """World-size-2 gloo run of TrainStep's communication logic with a fake engine (the CUDA path cannot run here): after the step each
+    rank's gradient arena holds the SUM over ranks on every bucket, and the Adam scale is 1/world."""
+    code = r'''
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, "%(root)s")
+from se3_diffusion_b200 import parallel
+rank = int(os.environ["RANK"])
+dist.init_process_group("gloo", rank=rank, world_size=2)
+class FakeEngine:
+    device = torch.device("cpu")
+    def train_bind(self, p, g): self.g = g
+    def train_forward(self, feats): return {}
+    def loss_forward(self, out, batch, conf): return {"total_loss": torch.tensor(float(rank))}
+    def loss_backward(self, out, batch, conf): return {}
+    def train_backward(self, dout, s0, s1):
+        lo, hi = parallel.grad_buckets()[s0]
+        self.g[lo:hi] += (rank + 1) * (s0 + 1)
+    def adam_step(self, p, g, m, v, step, lr, betas, eps, grad_scale): self.scale = grad_scale; self.snapshot = g.clone()
+import se3_diffusion_b200.engine as E
+parallel_flat = E.flat_from_state
+E.flat_from_state = lambda state, device: torch.zeros(E.arena_layout()[1])
+eng = FakeEngine()
+ts = parallel.TrainStep(eng, {}, lr=1e-3)
+torch.cuda.Event = lambda **k: type("Ev", (), {"record": lambda s: None, "synchronize": lambda s: None, "elapsed_time": lambda s, o: 0.0})()
+ts({}, {})
+ok = eng.scale == 0.5
+for s, (lo, hi) in enumerate(parallel.grad_buckets()):
+    ok = ok and bool(torch.all(eng.snapshot[lo:hi] == 3.0 * (s + 1)))
+print("DDP-LOGIC-OK" if ok else "DDP-LOGIC-BAD", rank)
+dist.destroy_process_group()
+''' % {"root": ROOT}
+    import socket
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        procs.append(subprocess.Popen([sys.executable, "-c", code], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True))
+    outs = [p.communicate(timeout=300) for p in procs]
+    for r, (o, e) in enumerate(outs):
+        assert f"DDP-LOGIC-OK {r}" in o, o + e
