@@ -43,6 +43,7 @@ def parse():
     p.add_argument("--cpu-steps", type=int, default=2, help="denoise steps of the bounded CPU sample")
     p.add_argument("--mode", default="sample", choices=["sample", "train"],
                    help="sample (default, the headline metric) | train: one optimiser step (fwd + DSM loss + bwd + all-reduce + Adam), BASELINE config 4")
+    p.add_argument("--sweep", action="store_true", help="measure the other BASELINE configs (C1 paper weights, C2, C5 length sweep) in one run")
     p.add_argument("--lr", type=float, default=1e-4)
     p.add_argument("--train-gemm", default="bf16x3", choices=["fp32", "bf16x3"], help="training-path GEMMs: CUDA-core fp32 or split-bf16 tensor cores")
     return p.parse_args()
@@ -288,6 +289,125 @@ def run_train(args):
         dist.destroy_process_group()
 
 
+def sample_line(args, eng, state, B, N, T, prec, world, rank, local, dist, torch, steps, warmup, tag, with_roofline=True, with_cpu=True, warm_T=None):
+    """One sampling measurement (value + e2e legs interleaved step by step) -> the JSON line dict (rank 0) or None."""
+    dev = torch.device("cuda", local)
+    first = rank * B
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    gathered = torch.empty(world * B, N, 37, 3, device=dev) if world > 1 else None
+    last = {}
+
+    def device_step(seed, num_t=T):
+        """inputs resident in HBM: prior drawn on the device, final coordinates stay in HBM (+ NCCL gather for N>1)."""
+        a37, rig, ms, nl = eng.sample_device(B, N, num_t=num_t, seed=seed, first_sample=first)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, a37)
+        last["a37"] = gathered if world > 1 else a37
+        return ms, nl
+
+    masks = {"res_mask": np.ones((B, N), np.float32), "fixed_mask": np.zeros((B, N), np.float32),
+             "seq_idx": np.tile(np.arange(1, N + 1, dtype=np.int32), (B, 1))}
+
+    def e2e_step(seed):
+        """public API with HOST buffers: init features H2D, final atom37/rigids/psi D2H into pinned memory."""
+        return eng.sample(B, N, num_t=T, seed=seed, first_sample=first, **masks)
+
+    for i in range(warmup):
+        device_step(1000 + i, warm_T or T)
+    barrier()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    dev_wall = e2e_wall = gpu_ms = 0.0
+    launches = 0
+    for i in range(steps):                    # the two legs interleaved: same clock / power state for both
+        barrier(); t0 = time.perf_counter()
+        ms, nl = device_step(2000 + i)
+        barrier(); dev_wall += time.perf_counter() - t0
+        gpu_ms += ms; launches += nl
+        barrier(); t0 = time.perf_counter()
+        e2e_step(2000 + i)
+        barrier(); e2e_wall += time.perf_counter() - t0
+    # the loop runs on the engine's own stream and is timed there with CUDA events (fd_sample_dev's gpu_ms); wall adds the host-side
+    # launch overhead and, for N>1, the NCCL gather — report the larger (honest) one, max over ranks
+    t = torch.tensor([max(dev_wall, gpu_ms / 1e3), e2e_wall], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    step_s, e2e_s = float(t[0]) / steps, float(t[1]) / steps
+    clk = clocks.stop() if rank == 0 else None
+    # checksum of global samples 0..min(32, B)-1 of the LAST timed step (seed 2000+steps-1): Philox keys are (seed, global sample id), so
+    # this number must be identical at 1, 2, 4 and 8 GPUs (SURVEY §8(e))
+    nchk = min(32, B)
+    chk = last["a37"][:nchk].double().sum().item() if rank == 0 else None
+    chk_abs = last["a37"][:nchk].double().abs().sum().item() if rank == 0 else None
+    if rank != 0:
+        return None
+    roof = None
+    if with_roofline:
+        from se3_diffusion_b200.synthetic import init_feats, random_frames
+        pk = peaks()
+        f = init_feats(random_frames(B, N, seed=0), t=0.5)
+        eng.forward(f, want_atoms=False); torch.cuda.synchronize(dev)
+        eng.stage_timing(True)
+        reps = 3
+        for _ in range(reps):
+            eng.forward(f, want_atoms=False)
+        torch.cuda.synchronize(dev)
+        st = eng.stage_times()
+        eng.stage_timing(False)
+        et_ms = st["edge_transition"][0] / reps / 3            # per EdgeTransition layer (3 per forward)
+        flops_layer = 524288.0 * B * N * N                     # executed FLOP/edge: 2*(128*384 + 384*384 + 512*128)
+        ach = flops_layer / (et_ms * 1e-3) / 1e12
+        fwd_ms = sum(v[0] for v in st.values()) / reps
+        passes = 3 if prec == "bf16x3" else 1
+        # dram__bytes_read+write of the kernel from one `ncu --set full` capture, regenerated by tools/ncu_traffic.sh; only used while the
+        # capture was taken from THIS library version (fd_version) and precision — otherwise null rather than a stale constant
+        traffic, tsrc = None, None
+        for name in sorted(os.listdir(os.path.join(ROOT, "profiles")), reverse=True):
+            if name.endswith("_fused_dram_traffic.json"):
+                tj = json.load(open(os.path.join(ROOT, "profiles", name)))
+                if tj.get("precision") == prec and tj.get("lib_version") == eng.lib.fd_version().decode():
+                    traffic, tsrc = tj["dram_bytes_per_edge"] * B * N * N, name
+                break
+        roof = {"bound": "tensor", "kernel": "tc_edge_fused_kernel (EdgeTransition: 3 chained GEMMs + LayerNorm, one launch per layer; stage also holds "
+                                             "the two O(N) node-term linears)",
+                "achieved": ach, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": ach / pk["bf16_tflops_sustained"],
+                "peak_source": pk["source"] + ", sustained bf16 figure (kernel timed inside a long step)",
+                "mma_passes": passes, "mma_issue_tflops": ach * passes, "mma_issue_frac_of_peak": ach * passes / pk["bf16_tflops_sustained"],
+                "note": "achieved = ALGORITHMIC FLOPs (524,288 per edge, DESIGN.md §4) / event time; in bf16x3 every product is three bf16 MMAs",
+                "traffic": traffic, "traffic_source": tsrc, "algorithmic_bytes_per_launch": (1024 if prec == "bf16x3" else 512) * B * N * N,
+                "ms_per_launch_group": et_ms, "algorithmic_flops_per_launch_group": flops_layer,
+                "share_of_forward": st["edge_transition"][0] / reps / fwd_ms,
+                "stage_ms_per_forward": {k: v[0] / reps for k, v in st.items()},
+                "end_to_end": {"reference_equivalent_flops_per_residue": (2248960.0 * N * N + 32421376.0 * N) * (T + 1) / N,
+                               "achieved_tflops_reference_equivalent": (2248960.0 * N * N + 32421376.0 * N) * (T + 1) * B / step_s / 1e12,
+                               "frac_of_sustained_bf16_peak": (2248960.0 * N * N + 32421376.0 * N) * (T + 1) * B / step_s / 1e12 / pk["bf16_tflops_sustained"]}}
+    value = world * B * N / step_s
+    e2e_v = world * B * N / e2e_s
+    cb = cpu_baseline(N, T, args.cpu_steps, state) if with_cpu else None
+    return {"metric": METRIC if (N == 256 and T == 500) else f"sampled backbone residues/sec (N={N}, {T} denoise steps)", "value": value,
+            "unit": "residues/s", "n_gpus": world, "steps": steps, "warmup": warmup,
+            "ms_per_step": step_s * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": {"fp32": "f32", "bf16x3": "bf16x3 (split bf16, fp32 accumulate)", "bf16": "bf16"}[prec],
+            "data": "synthetic (random-init weights of the FrameDiff architecture; Philox Gaussian/IGSO(3) prior + step noise)" if tag != "C1"
+                    else "weights/paper_weights.npz (the reference's shipped checkpoint); Philox prior + step noise",
+            "config": {"workload": f"{B} backbones/GPU x N={N} residues x {T} denoise steps ({tag})",
+                       "batch_per_gpu": B, "global_batch": world * B, "nres": N, "num_t": T, "precision": prec,
+                       "parallelism": f"batch-sharded dp{world}", "cuda_graph": True,
+                       "l2": "not flushed: each forward streams a %.0f MB edge tensor (> 126 MB L2)" % (B * N * N * 128 * 4 / 1e6)},
+            "e2e": {"value": e2e_v, "unit": "residues/s", "ms_per_step": e2e_s * 1e3,
+                    "h2d_bytes_per_step": int(sum(v.nbytes for v in masks.values())),
+                    "d2h_bytes_per_step": int(B * N * (111 + 7 + 2) * 4)},
+            "gpu_launches": int(launches), "gpu_ms_per_step_events": gpu_ms / steps,
+            "sample_checksum": {"samples": nchk, "seed": 2000 + steps - 1, "sum": chk, "abs_sum": chk_abs},
+            "clocks": clk, "roofline": roof, "cpu_baseline": cb}
+
+
 def main():
     args = parse()
     if args.impl == "reference":
@@ -307,126 +427,31 @@ def main():
     if world != args.gpus and rank == 0:
         print(f"[bench] warning: --gpus {args.gpus} but WORLD_SIZE={world}", file=sys.stderr)
     torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    B = args.batch or 32
-    N, T = args.nres, args.num_t
     prec = args.precision or os.environ.get("FD_PRECISION", "bf16x3")   # parity-grade tensor-core mode (1e-4 vs the fp32 reference)
     eng = FrameDiffEngine(local, prec)
     state = synthetic_state()
     eng.load_weights(state)
-    first = rank * B
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
-
-    gathered = torch.empty(world * B, N, 37, 3, device=dev) if world > 1 else None
-
-    def device_step(seed):
-        """inputs resident in HBM: prior drawn on the device, final coordinates stay in HBM (+ NCCL gather for N>1)."""
-        a37, rig, ms, nl = eng.sample_device(B, N, num_t=T, seed=seed, first_sample=first)
-        if world > 1:
-            dist.all_gather_into_tensor(gathered, a37)
-        return ms, nl
-
-    masks = {"res_mask": np.ones((B, N), np.float32), "fixed_mask": np.zeros((B, N), np.float32),
-             "seq_idx": np.tile(np.arange(1, N + 1, dtype=np.int32), (B, 1))}
-
-    def e2e_step(seed):
-        """public API with HOST buffers: init features H2D, final atom37/rigids/psi D2H into pinned memory."""
-        out = eng.sample(B, N, num_t=T, seed=seed, first_sample=first, **masks)
-        return out
-
-    # ---- warm-up ----------------------------------------------------------------------------------------------------
-    for i in range(args.warmup):
-        device_step(1000 + i)
-    barrier()
-    clocks = ClockSampler(local)
-    if rank == 0:
-        clocks.start()
-    # ---- timed: device-resident ---------------------------------------------------------------------------------------
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    t_wall0 = time.perf_counter()
-    gpu_ms, launches = 0.0, 0
-    for i in range(args.steps):
-        ms, nl = device_step(2000 + i)
-        gpu_ms += ms; launches += nl
-    barrier()
-    wall = time.perf_counter() - t_wall0
-    # the loop runs on the engine's own stream and is timed there with CUDA events (fd_sample_dev's gpu_ms); wall adds the
-    # host-side graph capture/launch overhead and, for N>1, the NCCL gather — report the larger (honest) one.
-    t = torch.tensor([max(wall, gpu_ms / 1e3)], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    step_s = float(t.item()) / args.steps
-    # ---- timed: end-to-end through the host API --------------------------------------------------------------------------
-    barrier()
-    t0 = time.perf_counter()
-    for i in range(args.steps):
-        e2e_step(3000 + i)
-    barrier()
-    te = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_s = float(te.item()) / args.steps
-    clk = clocks.stop() if rank == 0 else None
-
-    # ---- roofline of the dominant kernel: EdgeTransition (87 % of the reference's FLOPs) ----------------------------------
-    roof = None
-    if rank == 0:
-        from se3_diffusion_b200.synthetic import init_feats, random_frames
-        pk = peaks()
-        f = init_feats(random_frames(B, N, seed=0), t=0.5)
-        eng.forward(f, want_atoms=False); torch.cuda.synchronize(dev)
-        eng.stage_timing(True)
-        reps = 3
-        for _ in range(reps):
-            eng.forward(f, want_atoms=False)
-        torch.cuda.synchronize(dev)
-        st = eng.stage_times()
-        eng.stage_timing(False)
-        et_ms = st["edge_transition"][0] / reps / 3            # per EdgeTransition layer (3 per forward)
-        flops_layer = 524288.0 * B * N * N                     # executed FLOP/edge: 2*(128*384 + 384*384 + 512*128)
-        ach = flops_layer / (et_ms * 1e-3) / 1e12
-        fwd_ms = sum(v[0] for v in st.values()) / reps
-        passes = 3 if prec == "bf16x3" else 1
-        traffic = None
-        tpath = os.path.join(ROOT, "profiles", "r1_fused_dram_traffic.json")
-        if os.path.exists(tpath):      # dram__bytes_read+write of tc_edge_fused_kernel from one `ncu --set full` capture (bytes per edge)
-            tj = json.load(open(tpath))
-            if tj.get("precision") == prec:
-                traffic = tj["dram_bytes_per_edge"] * B * N * N
-        roof = {"bound": "tensor", "kernel": "tc_edge_fused_kernel (EdgeTransition: 3 chained GEMMs + LayerNorm, one launch per layer; stage also holds "
-                                             "the two O(N) node-term linears)",
-                "achieved": ach, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": ach / pk["bf16_tflops_sustained"],
-                "peak_source": pk["source"] + ", sustained bf16 figure (kernel timed inside a long step)",
-                "mma_passes": passes, "mma_issue_tflops": ach * passes, "mma_issue_frac_of_peak": ach * passes / pk["bf16_tflops_sustained"],
-                "note": "achieved = ALGORITHMIC FLOPs (524,288 per edge, DESIGN.md §4) / event time; in bf16x3 every product is three bf16 MMAs",
-                "traffic": traffic, "algorithmic_bytes_per_launch": (1024 if prec == "bf16x3" else 512) * B * N * N,
-                "ms_per_launch_group": et_ms, "algorithmic_flops_per_launch_group": flops_layer,
-                "share_of_forward": st["edge_transition"][0] / reps / fwd_ms,
-                "stage_ms_per_forward": {k: v[0] / reps for k, v in st.items()}}
-
-    if rank == 0:
-        value = world * B * N / step_s
-        e2e_v = world * B * N / e2e_s
-        cb = None if args.no_cpu_baseline else cpu_baseline(N, T, args.cpu_steps, state)
-        line = {"metric": METRIC, "value": value, "unit": "residues/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": step_s * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": {"fp32": "f32", "bf16x3": "bf16x3 (split bf16, fp32 accumulate)", "bf16": "bf16"}[prec],
-                "data": "synthetic (random-init weights of the FrameDiff architecture; Philox Gaussian/IGSO(3) prior + step noise)",
-                "config": {"workload": f"{B} backbones/GPU x N={N} residues x {T} denoise steps (BASELINE config 3 per-GPU shard)",
-                           "batch_per_gpu": B, "global_batch": world * B, "nres": N, "num_t": T, "precision": prec,
-                           "parallelism": f"batch-sharded dp{world}", "cuda_graph": True,
-                           "l2": "not flushed: each forward streams a %.0f MB edge tensor (> 126 MB L2)" % (B * N * N * 128 * 4 / 1e6)},
-                "e2e": {"value": e2e_v, "unit": "residues/s", "ms_per_step": e2e_s * 1e3,
-                        "h2d_bytes_per_step": int(sum(v.nbytes for v in masks.values())),
-                        "d2h_bytes_per_step": int(B * N * (111 + 7 + 2) * 4)},
-                "gpu_launches": int(launches), "gpu_ms_per_step_events": gpu_ms / args.steps,
-                "clocks": clk, "roofline": roof, "cpu_baseline": cb}
-        print(json.dumps(line), flush=True)
+    if args.sweep:
+        # the other BASELINE configs (builder-run; JSON kept under profiles/): C1 with the shipped checkpoint, C2, and the C5 length sweep
+        lines = []
+        wpath = os.path.join(ROOT, "weights", "paper_weights.npz")
+        cfgs = [("C2: BASELINE config 2", 32, 128, 500, 2)] + [(f"C5: length sweep N={n}", 32, n, 500, 1) for n in (100, 200, 300, 400, 512)]
+        if os.path.exists(wpath):
+            eng.load_weights(dict(np.load(wpath)))
+            ln = sample_line(args, eng, state, 1, 60, 50, prec, world, rank, local, dist, torch, 5, 3, "C1", with_cpu=False)
+            if ln: lines.append(ln)
+            eng.load_weights(state)
+        for tag, B, N, T, steps in cfgs:
+            ln = sample_line(args, eng, state, B, N, T, prec, world, rank, local, dist, torch, steps, 3, tag, with_cpu=False, warm_T=10)
+            if ln: lines.append(ln)
+        if rank == 0:
+            print(json.dumps({"sweep": lines}), flush=True)
+    else:
+        B = args.batch or 32
+        line = sample_line(args, eng, state, B, args.nres, args.num_t, prec, world, rank, local, dist, torch, args.steps, args.warmup,
+                           "BASELINE config 3 per-GPU shard" if (B == 32 and args.nres == 256) else "custom", with_cpu=not args.no_cpu_baseline)
+        if rank == 0:
+            print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 

@@ -51,7 +51,7 @@ struct DevGuard {
 };
 
 extern "C" const char* fd_last_error(void) { return g_err; }
-extern "C" const char* fd_version(void) { return "framediff_b200 0.1 (sm_100a)"; }
+extern "C" const char* fd_version(void) { return "framediff_b200 0.2 (sm_100a)"; }
 
 // ------------------------------------------------------------------------------------------------------------------
 // stages (for bench.py's breakdown)
