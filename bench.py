@@ -147,6 +147,19 @@ def run_reference(args):
         return
     from oracle import framediff_oracle as fo      # this arm never touches the product package or its .so
     state = fo.synthetic_weights(0)
+    if args.mode == "train":                       # the reference's training step on the host (autograd through the port + torch Adam)
+        vals, last = [], None
+        for i in range(args.warmup + args.steps):
+            last = cpu_train_baseline(args.nres, state)
+            if i >= args.warmup:
+                vals.append(last["value"])
+        v = float(np.mean(vals)); cb = dict(last); cb["value"] = v
+        print(json.dumps({"impl": "reference", "metric": TRAIN_METRIC, "value": v, "unit": "examples/s", "n_gpus": args.gpus, "steps": args.steps,
+                          "warmup": args.warmup, "ms_per_step": 1e3 / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                          "data": "synthetic (random-init weights; one noised example)", "config": {"workload": f"train step, 1 example x N={args.nres}, CPU"},
+                          "cpu_baseline": cb, "e2e": {"value": v, "unit": "examples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                          "gpu_launches": 0}), flush=True)
+        return
     args.cpu_steps = max(args.cpu_steps, 10)       # at least 10 denoise steps per bounded sample
     times = []
     last = None

@@ -135,6 +135,21 @@ int fd_forward_marginal(fd_handle h, int64_t n, const float* rigids_0, double t,
                         const double* z_trans, const float* diffuse_mask, float* rigids_t, double* rot_score, double* trans_score,
                         double* rot_score_scaling, double* trans_score_scaling, void* stream);
 
+/* Batched, padded training-data assembly (data/pdb_data_loader.py:251-272 noises ONE example per DataLoader worker call,
+ * data/utils.py:387-399 pads): forward_marginal of B examples padded to N residues, example b at its own time t_host[b] (HOST array),
+ * res_mask [B,N] marks real residues (they are the diffused ones, as in the loader); padded rows come back all-zero like du.pad_feats.
+ * Draws z_axis/u_angle/z_trans [B,N,*] fp64 device (values on padded rows are ignored).  Scalings: HOST arrays [B] (may be NULL). */
+int fd_forward_marginal_batch(fd_handle h, int B, int N, const float* rigids_0, const double* t_host, const double* z_axis,
+                              const double* u_angle, const double* z_trans, const float* res_mask, float* rigids_t, double* rot_score,
+                              double* trans_score, double* rot_score_scaling_host, double* trans_score_scaling_host, void* stream);
+
+/* Intermittent eval metrics (analysis/metrics.py:120-132 ca_ca_distance, ca_ca_clashes) for B backbones on the device:
+ * ca [B,N,3] fp32 (Angstrom), n_valid [B] int32 residues used per backbone (NULL = N); out4 [B,4] fp64 device =
+ * { ca_ca_bond_dev, ca_ca_valid_percent, num_ca_steric_clashes, ca_steric_clash_percent } with the reference's tolerances
+ * tol_bond = 0.1, tol_clash = 1.5 passed by the caller. */
+int fd_ca_metrics(fd_handle h, int B, int N, const float* ca, const int32_t* n_valid, double tol_bond, double tol_clash, double* out4,
+                  void* stream);
+
 /* SE3Diffuser.score_scaling (se3_diffuser.py:155-158): host scalars. */
 int fd_score_scaling(fd_handle h, double t, double* rot_scaling, double* trans_scaling);
 

@@ -858,3 +858,23 @@ def loss_terms(model_out, batch, exp_conf=None, diffuse_trans=True, diffuse_rot=
     return {"batch_train_loss": final, "batch_rot_loss": rot_loss, "batch_trans_loss": trans_loss, "batch_bb_atom_loss": bb_atom_loss,
             "batch_dist_mat_loss": dist_mat_loss, "total_loss": norm(final), "rot_loss": norm(rot_loss), "trans_loss": norm(trans_loss),
             "bb_atom_loss": norm(bb_atom_loss), "dist_mat_loss": norm(dist_mat_loss)}
+
+
+# --------------------------------------------------------------------------------------------------------------
+# Intermittent eval metrics (analysis/metrics.py:120-132) — the checker of fd_ca_metrics
+# --------------------------------------------------------------------------------------------------------------
+CA_CA = 3.80209737096          # data/residue_constants.py:29
+
+
+def ca_ca_distance(ca_pos, tol=0.1):
+    """analysis/metrics.py:120-125."""
+    d = np.linalg.norm(ca_pos - np.roll(ca_pos, 1, axis=0), axis=-1)[1:]
+    return np.mean(np.abs(d - CA_CA)), np.mean(d < (CA_CA + tol))
+
+
+def ca_ca_clashes(ca_pos, tol=1.5):
+    """analysis/metrics.py:127-132."""
+    d2 = np.linalg.norm(ca_pos[:, None, :] - ca_pos[None, :, :], axis=-1)
+    inter = d2[np.where(np.triu(d2, k=0) > 0)]
+    cl = inter < tol
+    return np.sum(cl), np.mean(cl)

@@ -79,6 +79,9 @@ SYMBOLS = {
                                   C.c_double, c_voidp, c_voidp, C.c_uint64, C.c_int64, C.c_int, c_voidp, c_voidp]),
     "fd_forward_marginal": (C.c_int, [c_voidp, C.c_int64, c_voidp, C.c_double, c_voidp, c_voidp, c_voidp, c_voidp, c_voidp, c_voidp, c_voidp,
                                       c_f64p, c_f64p, c_voidp]),
+    "fd_forward_marginal_batch": (C.c_int, [c_voidp, C.c_int, C.c_int, c_voidp, c_voidp, c_voidp, c_voidp, c_voidp, c_voidp, c_voidp, c_voidp, c_voidp,
+                                            c_voidp, c_voidp, c_voidp]),
+    "fd_ca_metrics": (C.c_int, [c_voidp, C.c_int, C.c_int, c_voidp, c_voidp, C.c_double, C.c_double, c_voidp, c_voidp]),
     "fd_score_scaling": (C.c_int, [c_voidp, C.c_double, c_f64p, c_f64p]),
     "fd_compute_backbone": (C.c_int, [c_voidp, C.c_int64, c_voidp, c_voidp, c_voidp, c_voidp, c_voidp]),
     "fd_sample_host": (C.c_int, [c_voidp, C.POINTER(SampleCfg), C.POINTER(SampleIn), C.POINTER(SampleOut)]),

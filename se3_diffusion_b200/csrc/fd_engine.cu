@@ -957,6 +957,54 @@ extern "C" int fd_forward_marginal(fd_handle h, int64_t n, const float* rigids_0
   return FD_OK;
 }
 
+// Batched, padded training-data assembly: forward_marginal of B examples at their own times t[b] in one call, with the
+// zero padding of du.pad_feats (data/utils.py:387-399) — what data/pdb_data_loader.py:251-272 + length_batching do per example on CPU workers.
+extern "C" int fd_forward_marginal_batch(fd_handle h, int B, int N, const float* rigids_0, const double* t_host, const double* z_axis,
+                                         const double* u_angle, const double* z_trans, const float* res_mask, float* rigids_t, double* rot_score,
+                                         double* trans_score, double* rot_score_scaling_host, double* trans_score_scaling_host, void* stream) {
+  if (!h || B < 1 || N < 1 || !rigids_0 || !t_host || !z_axis || !u_angle || !z_trans || !res_mask || !rigids_t || !rot_score || !trans_score)
+    return fail(FD_EINVAL, "fd_forward_marginal_batch: bad argument");
+  for (int b = 0; b < B; ++b)
+    if (!(t_host[b] >= 0.0 && t_host[b] <= 1.0)) return fail(FD_EINVAL, "Invalid t=%g", t_host[b]);
+  DevGuard dev_guard(h->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  for (int b = 0; b < B; ++b) {
+    const double t = t_host[b];
+    const int idx = sigma_idx_host(h->h_sigma_grid, t);
+    auto it = h->igso3_rows.find(idx);
+    if (it == h->igso3_rows.end()) {
+      std::vector<double> cdf(SO3_NOMEGA);
+      double scal = 0;
+      CKI(build_igso3_rows(h, 1, &idx, nullptr, cdf.data(), nullptr, &scal));
+      double* d = nullptr;
+      CK(cudaMalloc(&d, SO3_NOMEGA * sizeof(double)));
+      CK(cudaMemcpy(d, cdf.data(), SO3_NOMEGA * sizeof(double), cudaMemcpyHostToDevice));
+      it = h->igso3_rows.emplace(idx, std::make_pair(d, scal)).first;
+    }
+    const long long o = (long long)b * N;
+    forward_marginal_kernel<<<(unsigned)((N + 7) / 8), 256, 0, st>>>(rigids_0 + o * 7, z_axis + o * 3, u_angle + o, z_trans + o * 3, res_mask + o, t,
+                                                                   h->h_sigma_grid[idx], it->second.first, h->d_omega, rigids_t + o * 7,
+                                                                   rot_score + o * 3, trans_score + o * 3, N, res_mask + o);
+    CK(cudaGetLastError());
+    if (rot_score_scaling_host) rot_score_scaling_host[b] = it->second.second;
+    if (trans_score_scaling_host) {
+      const double beta = t * R3_MIN_B + 0.5 * (t * t) * (R3_MAX_B - R3_MIN_B);
+      trans_score_scaling_host[b] = 1.0 / sqrt(1.0 - exp(-beta));
+    }
+  }
+  return FD_OK;
+}
+
+// analysis/metrics.py:120-132 on the device: per-backbone CA-CA bond deviation / valid fraction / steric clashes.
+extern "C" int fd_ca_metrics(fd_handle h, int B, int N, const float* ca, const int32_t* n_valid, double tol_bond, double tol_clash, double* out4,
+                             void* stream) {
+  if (!h || B < 1 || N < 1 || !ca || !out4) return fail(FD_EINVAL, "fd_ca_metrics: bad argument");
+  DevGuard dev_guard(h->device);
+  ca_metrics_kernel<<<B, 256, 0, static_cast<cudaStream_t>(stream)>>>(ca, n_valid, tol_bond, tol_clash, out4, N);
+  CK(cudaGetLastError());
+  return FD_OK;
+}
+
 // SE3Diffuser.score_scaling (data/se3_diffuser.py:155-158): (rot, trans) scalings at time t; the IGSO(3) row is built on the GPU.
 extern "C" int fd_score_scaling(fd_handle h, double t, double* rot_scaling, double* trans_scaling) {
   if (!h) return fail(FD_EINVAL, "null handle");

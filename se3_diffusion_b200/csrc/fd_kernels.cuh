@@ -1129,10 +1129,15 @@ __global__ void __launch_bounds__(256) forward_marginal_kernel(
     const float* __restrict__ rigids0, const double* __restrict__ z_axis, const double* __restrict__ u_angle,
     const double* __restrict__ z_trans, const float* __restrict__ diffuse_mask, double t, double sigma, const double* __restrict__ cdf,
     const double* __restrict__ omega_grid, float* __restrict__ rigids_t, double* __restrict__ rot_score, double* __restrict__ trans_score,
-    long long n) {
+    long long n, const float* __restrict__ pad_mask = nullptr /* batched assembly: rows with pad_mask == 0 are padding -> all outputs zero */) {
   const int lane = threadIdx.x & 31;
   const long long r = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (r >= n) return;
+  if (pad_mask && pad_mask[r] == 0.f) {     // du.pad_feats (data/utils.py:387-399) pads every feature with zeros after the noising
+    if (lane < 3) { rot_score[r * 3 + lane] = 0.0; trans_score[r * 3 + lane] = 0.0; }
+    if (lane < 7) rigids_t[r * 7 + lane] = 0.f;
+    return;
+  }
   const double ax0 = z_axis[r * 3], ax1 = z_axis[r * 3 + 1], ax2 = z_axis[r * 3 + 2];
   const double an = sqrt(ax0 * ax0 + ax1 * ax1 + ax2 * ax2);
   const double u = u_angle[r];

@@ -1029,6 +1029,43 @@ __global__ void __launch_bounds__(256) loss_backward_kernel(const LossBwdArgs a)
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+// Intermittent eval metrics on the device (analysis/metrics.py:120-132 ca_ca_distance / ca_ca_clashes): per backbone
+//   out[b] = { mean |d_i - 3.80209737096|, fraction of bonds d_i < 3.802 + tol_bond, number of CA pairs closer than tol_clash,
+//              fraction of such pairs among the pairs with distance > 0 }       d_i = |CA_i - CA_{i-1}|, valid residues first (mask prefix)
+// ca [B,N,3] fp32 (Angstrom); n_valid[b] residues are used (the reference slices the unpadded chain before calling these functions).
+// One CTA per backbone; fp64 accumulation like numpy's float64 means.
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) ca_metrics_kernel(const float* __restrict__ ca, const int* __restrict__ n_valid, double tol_bond, double tol_clash,
+                                                         double* __restrict__ out, int N) {
+  __shared__ double red[8];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const int n = n_valid ? min(n_valid[b], N) : N;
+  const float* x = ca + (long long)b * N * 3;
+  const double CA_CA = 3.80209737096;
+  double dev = 0.0, valid = 0.0;
+  for (int i = 1 + tid; i < n; i += 256) {
+    const float dx = x[i * 3] - x[(i - 1) * 3], dy = x[i * 3 + 1] - x[(i - 1) * 3 + 1], dz = x[i * 3 + 2] - x[(i - 1) * 3 + 2];
+    const float d = sqrtf(dx * dx + dy * dy + dz * dz);        // np.linalg.norm of a float32 array stays float32
+    dev += fabs((double)d - CA_CA);
+    valid += (double)d < CA_CA + tol_bond ? 1.0 : 0.0;
+  }
+  double clashes = 0.0, pairs = 0.0;
+  for (long long p = tid; p < (long long)n * n; p += 256) {
+    const int i = (int)(p / n), j = (int)(p - (long long)i * n);
+    if (j < i) continue;                                        // np.triu(k=0); the diagonal has distance 0 and is dropped by `> 0`
+    const float dx = x[i * 3] - x[j * 3], dy = x[i * 3 + 1] - x[j * 3 + 1], dz = x[i * 3 + 2] - x[j * 3 + 2];
+    const float d = sqrtf(dx * dx + dy * dy + dz * dz);
+    if (d > 0.f) { pairs += 1.0; clashes += (double)d < tol_clash ? 1.0 : 0.0; }
+  }
+  dev = block_sum_f64_t(dev, red); valid = block_sum_f64_t(valid, red);
+  clashes = block_sum_f64_t(clashes, red); pairs = block_sum_f64_t(pairs, red);
+  if (tid == 0) {
+    const double nb = n > 1 ? (double)(n - 1) : 1.0;
+    out[b * 4 + 0] = dev / nb; out[b * 4 + 1] = valid / nb; out[b * 4 + 2] = clashes; out[b * 4 + 3] = pairs > 0.0 ? clashes / pairs : 0.0;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
 // Adam (torch.optim.Adam defaults of the reference: betas (0.9, 0.999), eps 1e-8, no weight decay, no amsgrad;
 // experiments/train_se3_diffusion.py:139-141) over the flat parameter arena.  skip[i] != 0 marks elements of parameters that
 // received no gradient this step (the reference's unused parameters keep grad None and are skipped by the optimiser).

@@ -291,6 +291,40 @@ def _forward_marginal(self, rigids_0: torch.Tensor, t: float, z_axis, u_angle, z
     return {"rigids_t": rt, "rot_score": rs, "trans_score": ts, "rot_score_scaling": a.value, "trans_score_scaling": b.value}
 
 
+def _forward_marginal_batch(self, rigids_0: torch.Tensor, t, z_axis, u_angle, z_trans, res_mask):
+    """fd_forward_marginal_batch: noises a padded batch [B,N,7] in one call, example b at time t[b]; padded rows (res_mask 0) come back zero like
+    du.pad_feats.  Returns the loader's feature dict for the batch (device tensors; scalings as float64 tensors [B])."""
+    dev = self.device
+    r0 = torch.as_tensor(rigids_0).to(dev, torch.float32).contiguous()
+    B, N = r0.shape[:2]
+    d64 = lambda a: torch.as_tensor(np.ascontiguousarray(a, dtype=np.float64)).to(dev)
+    za, ua, zt = d64(z_axis), d64(u_angle), d64(z_trans)
+    rm = torch.as_tensor(np.ascontiguousarray(res_mask, dtype=np.float32)).to(dev)
+    th = np.ascontiguousarray(t, dtype=np.float64).reshape(B)
+    rt = torch.empty(B, N, 7, device=dev, dtype=torch.float32)
+    rs = torch.empty(B, N, 3, device=dev, dtype=torch.float64)
+    ts = torch.empty(B, N, 3, device=dev, dtype=torch.float64)
+    a, b = np.empty(B), np.empty(B)
+    st = torch.cuda.current_stream(dev)
+    check(self.lib.fd_forward_marginal_batch(self._h, B, N, _ptr(r0), _np_ptr(th), _ptr(za), _ptr(ua), _ptr(zt), _ptr(rm), _ptr(rt), _ptr(rs), _ptr(ts),
+                                             _np_ptr(a), _np_ptr(b), C.c_void_p(st.cuda_stream)))
+    self._fm_keep = (r0, za, ua, zt, rm)
+    return {"rigids_t": rt, "rot_score": rs, "trans_score": ts, "rot_score_scaling": torch.tensor(a), "trans_score_scaling": torch.tensor(b),
+            "t": torch.tensor(th)}
+
+
+def _ca_metrics(self, ca: torch.Tensor, n_valid=None, tol_bond: float = 0.1, tol_clash: float = 1.5) -> Dict[str, torch.Tensor]:
+    """analysis/metrics.py:120-132 for a batch of CA traces [B,N,3] on the device."""
+    dev = self.device
+    x = torch.as_tensor(ca).to(dev, torch.float32).contiguous()
+    B, N = x.shape[:2]
+    nv = None if n_valid is None else torch.as_tensor(n_valid).to(dev, torch.int32).contiguous()
+    out = torch.empty(B, 4, device=dev, dtype=torch.float64)
+    st = torch.cuda.current_stream(dev)
+    check(self.lib.fd_ca_metrics(self._h, B, N, _ptr(x), _ptr(nv), float(tol_bond), float(tol_clash), _ptr(out), C.c_void_p(st.cuda_stream)))
+    return {"ca_ca_bond_dev": out[:, 0], "ca_ca_valid_percent": out[:, 1], "num_ca_steric_clashes": out[:, 2], "ca_steric_clash_percent": out[:, 3]}
+
+
 def _score_scaling(self, t: float):
     a, b = C.c_double(0), C.c_double(0)
     check(self.lib.fd_score_scaling(self._h, float(t), C.byref(a), C.byref(b)))
@@ -333,6 +367,8 @@ def _inference_fn(self, data_init: dict, num_t: int = 500, min_t: float = 0.01, 
 
 
 FrameDiffEngine.forward_marginal = _forward_marginal
+FrameDiffEngine.forward_marginal_batch = _forward_marginal_batch
+FrameDiffEngine.ca_metrics = _ca_metrics
 FrameDiffEngine.score_scaling = _score_scaling
 FrameDiffEngine.inference_fn = _inference_fn
 

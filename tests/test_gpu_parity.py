@@ -655,3 +655,53 @@ def test_loss_forward_vs_reference_loss_fn(eng, tag):
     ours = eng.forward(f)
     got2 = eng.loss_forward(ours, batch)
     assert_close(got2["batch_train_loss"].cpu().numpy(), g["aux_batch_train_loss"], 5e-4, name="loss from our forward")
+
+
+# ---- batched training-data assembly and eval metrics on the device -------------------------------------------
+def test_forward_marginal_batch_padded_vs_single_and_oracle(eng):
+    """fd_forward_marginal_batch (one call for a padded batch, per-example t) == the per-example kernel on the unpadded chains, zeros on the
+    padding (du.pad_feats), and the oracle's forward_marginal on one of them."""
+    rs = np.random.RandomState(8)
+    B, N = 3, 40
+    lens = [40, 33, 21]
+    ts = [0.7, 0.31, 0.05]
+    r0 = np.zeros((B, N, 7), np.float32); mask = np.zeros((B, N), np.float32)
+    za, ua, zt = rs.standard_normal((B, N, 3)), rs.uniform(size=(B, N)), rs.standard_normal((B, N, 3))
+    for b, n in enumerate(lens):
+        q = rs.standard_normal((n, 4)); q /= np.linalg.norm(q, axis=-1, keepdims=True)
+        r0[b, :n, :4] = q; r0[b, :n, 4:] = rs.standard_normal((n, 3)) * 8; mask[b, :n] = 1
+    out = eng.forward_marginal_batch(torch.tensor(r0), ts, za, ua, zt, mask)
+    for b, n in enumerate(lens):
+        one = eng.forward_marginal(torch.tensor(r0[b, :n]), ts[b], za[b, :n], ua[b, :n], zt[b, :n])
+        for k in ("rigids_t", "rot_score", "trans_score"):
+            assert np.array_equal(out[k][b, :n].cpu().numpy(), one[k].cpu().numpy()), (b, k)          # same kernel: bit-exact
+            assert float(out[k][b, n:].abs().sum()) == 0.0, (b, k)                                     # zero padding
+        assert out["rot_score_scaling"][b] == one["rot_score_scaling"] and out["trans_score_scaling"][b] == one["trans_score_scaling"]
+    # against the oracle (numpy RNG feeding both): example 0
+    np.random.seed(3)
+    n = lens[0]
+    z1, u1 = np.random.randn(n, 3), np.random.rand(n)
+    np.random.seed(3)
+    ref = fo.forward_marginal(torch.tensor(r0[0, :n]).double(), ts[0])
+    # the oracle draws the translation noise as normal(loc, scale): reproduce the standard normal it consumed
+    np.random.seed(3); np.random.randn(n, 3); np.random.rand(n); z3 = np.random.normal(size=(n, 3))
+    o1 = eng.forward_marginal_batch(torch.tensor(r0[:1]), ts[:1], z1[None].repeat(1, 0) if False else np.pad(z1, ((0, N - n), (0, 0)))[None],
+                                    np.pad(u1, (0, N - n))[None], np.pad(z3, ((0, N - n), (0, 0)))[None], mask[:1])
+    assert_close(o1["rot_score"][0, :n].cpu().numpy(), ref["rot_score"], 0, norm_rel=1e-6, name="rot_score vs oracle")
+    assert_close(fo.quat_to_rotmat(o1["rigids_t"][0, :n, :4].cpu()).numpy(), fo.quat_to_rotmat(torch.as_tensor(ref["rigids_t"])[..., :4].float()).numpy(), 0,
+                 atol=5e-6, name="rot_t vs oracle")
+
+
+def test_ca_metrics_vs_oracle_and_reference_golden(eng):
+    g = golden("metrics")
+    N = 128
+    ca = np.zeros((3, N, 3), np.float32); nv = []
+    for k in range(3):
+        x = g[f"ca_{k}"]; ca[k, :len(x)] = x; nv.append(len(x))
+    m = eng.ca_metrics(torch.tensor(ca), nv)
+    got = np.stack([m[k].cpu().numpy() for k in ("ca_ca_bond_dev", "ca_ca_valid_percent", "num_ca_steric_clashes", "ca_steric_clash_percent")], -1)
+    for k in range(3):
+        assert_close(got[k], g[f"ref_{k}"], 1e-6, atol=1e-9, name=f"metrics {k} vs the reference functions")
+        dev, valid = fo.ca_ca_distance(ca[k, :nv[k]]); ncl, pcl = fo.ca_ca_clashes(ca[k, :nv[k]])
+        assert_close(got[k], np.array([dev, valid, ncl, pcl], dtype=np.float64), 1e-6, atol=1e-9, name=f"metrics {k} vs oracle")
+        assert got[k][2] == g[f"ref_{k}"][2]                                                          # clash COUNT: integer, bit-exact

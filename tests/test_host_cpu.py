@@ -169,7 +169,7 @@ def test_product_code_never_imports_the_oracle():
     allowed = [src.index("def cpu_baseline"), src.index("def run_reference")] if "def cpu_baseline" in src else []
     for pos in legs:        # every oracle import sits inside the CPU-baseline or the reference-arm function
         fn_start = max(m.start() for m in re.finditer(r"^def \w+", src[:pos], re.M))
-        assert src[fn_start:fn_start + 40].startswith(("def cpu_baseline", "def run_reference")), src[fn_start:fn_start + 60]
+        assert src[fn_start:fn_start + 40].startswith(("def cpu_baseline", "def cpu_train_baseline", "def run_reference")), src[fn_start:fn_start + 60]
 
 
 def test_grad_buckets_partition_the_arena():
