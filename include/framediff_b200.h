@@ -278,6 +278,12 @@ typedef struct {
  * computes.  Stages must run in order 0..3; (0,3) runs the whole backward. */
 int fd_train_backward(fd_handle h, const fd_train_grads* dout, int stage_first, int stage_last, void* stream);
 int fd_train_release(fd_handle h);
+/* Workspace query: bytes of device memory the handle allocates for a (B, N) problem (estimate within a few per cent: the
+ * arenas add 256-byte alignment per buffer).  which = 0 inference workspace in the current precision mode, 1 sampling-loop buffers for
+ * num_t steps (aux != 0: with the per-step trajectories), 2 training tape + backward scratch.  The handle owns these arenas (allocated on
+ * first use for a shape, reused until the shape changes); all other buffers are the caller's. */
+int64_t fd_workspace_bytes(fd_handle h, int which, int B, int N, int num_t, int aux);
+int64_t fd_debug_alloc_bytes(fd_handle h, int which);   /* developer aid: bytes of the arena `which` as currently allocated (0 = none) */
 /* Arithmetic of the training path's GEMMs: 0 = fp32 on the CUDA cores (default), 1 = split-bf16 (hi*hi + hi*lo + lo*hi, fp32 accumulate)
  * on the tensor cores — the accuracy class of FD_PREC_BF16X3; both meet the gradient tolerances of tests/test_gpu_train.py. */
 int fd_train_set_gemm(fd_handle h, int mode);

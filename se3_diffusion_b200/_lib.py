@@ -99,6 +99,8 @@ SYMBOLS = {
     "fd_train_forward": (C.c_int, [c_voidp, C.c_int, C.c_int, C.POINTER(ForwardIn), C.POINTER(ForwardOut), c_voidp]),
     "fd_train_backward": (C.c_int, [c_voidp, C.POINTER(TrainGrads), C.c_int, C.c_int, c_voidp]),
     "fd_train_release": (C.c_int, [c_voidp]),
+    "fd_workspace_bytes": (C.c_int64, [c_voidp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "fd_debug_alloc_bytes": (C.c_int64, [c_voidp, C.c_int]),
     "fd_train_set_gemm": (C.c_int, [c_voidp, C.c_int]),
     "fd_loss_backward": (C.c_int, [c_voidp, C.c_int, C.c_int, c_voidp, c_voidp, C.POINTER(TrainGradsOut), c_voidp]),
     "fd_adam_step": (C.c_int, [c_voidp, c_voidp, c_voidp, c_voidp, c_voidp, C.c_int64, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int64,

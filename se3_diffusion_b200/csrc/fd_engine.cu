@@ -1387,6 +1387,44 @@ extern "C" int fd_train_backward(fd_handle h, const fd_train_grads* dout, int st
   DevGuard dev_guard(h->device);
   return train_backward_impl(h, h->train, dout, stage_first, stage_last, (cudaStream_t)stream);
 }
+// Device memory the handle allocates for a (B, N) problem: which = 0 inference workspace (current precision mode), 1 sampling-loop buffers
+// (num_t steps, aux_traj trajectories if aux != 0), 2 training tape.  SURVEY §8(b) lists a workspace query; the handle owns these arenas.
+extern "C" int64_t fd_workspace_bytes(fd_handle h, int which, int B, int N, int num_t, int aux) {
+  if (!h || B < 1 || N < 1) return FD_EINVAL;
+  const size_t R = (size_t)B * N, E = R * N, Np = (size_t)((N + 3) & ~3);
+  if (which == 0) {
+    const bool tc = h->precision != FD_PREC_FP32;
+    const size_t chunk = E < ((size_t)1 << 18) ? E : ((size_t)1 << 18);
+    size_t fl = R * (NODE_IN_PAD + 256 + 5 * C_S + 4 * TF_D + 3 * TF_D + PROJ_ALL + 2 * H * PQ * 3 + 2 * H * PV * 3 + IPA_FEAT + 7 + C_Z + ET_NODE + C_S) +
+                (size_t)B * 32 + (tc ? R * H * C_Z : 0) + (size_t)B * (TF_H + H) * N * Np + E * C_Z + (tc ? 0 : chunk * (2 * ET_HID + C_Z));
+    return (int64_t)(fl * sizeof(float) + (tc ? tc_workspace_bytes(B, N) : 0));
+  }
+  if (which == 1) {
+    const size_t T = (size_t)(num_t > 0 ? num_t : 1);
+    size_t by = R * (7 * 4 * 3 + 3 * 4 + 2 * 4 + 2 * 4 + 2 * 4 + 111 * 4 * 2 + 4 + 2 * 3 * 8) + T * (sizeof(StepSched) + 8);
+    if (aux) by += T * R * (111 * 4 * 2 + 3 * 4) + (T + 1) * R * 7 * 4;
+    return (int64_t)by;
+  }
+  if (which == 2) {
+    const size_t AT = (size_t)B * H * N * Np, PT = (size_t)B * TF_H * N * Np;
+    size_t fl = R * (NODE_IN_PAD + 4 * 256 + 7 + 2 * C_S) + E * (EDGE_IN + 3 * C_Z) +                                                   // embedders, heads
+                R * (5 * C_S + 3 * TF_D + 3 * TF_D + IPA_FEAT + PROJ_ALL + 7 + 2 * H * C_Z + 4 * H * PQ * 3 + 2 * H * PV * 3 + 2 * ET_HID + 3 * C_Z) + PT + AT +
+                E * (4 * C_Z + 2 * ET_HID + H) +                                                                                       // backward scratch
+                NBLK * (E * C_Z + R * (PROJ_ALL + 7 + 2 * H * PQ * 3 + 2 * H * PV * 3 + H * C_Z + IPA_FEAT + 6 * C_S + (TF_LAYERS + 1) * TF_D +
+                                       TF_LAYERS * (3 * TF_D + 6 * TF_D)) + AT + TF_LAYERS * PT) +
+                (NBLK - 1) * (R * (C_Z + ET_NODE) + E * (2 * ET_HID + C_Z));
+    return (int64_t)(fl * sizeof(float));
+  }
+  return FD_EINVAL;
+}
+// actual size of the arena currently allocated (0 if none): lets tests check fd_workspace_bytes against what the handle really allocated
+extern "C" int64_t fd_debug_alloc_bytes(fd_handle h, int which) {
+  if (!h) return FD_EINVAL;
+  if (which == 0) return (int64_t)h->ws.bytes;
+  if (which == 1) return (int64_t)h->lb.bytes;
+  if (which == 2) return h->train ? (int64_t)h->train->tape.bytes : 0;
+  return FD_EINVAL;
+}
 extern "C" int fd_train_set_gemm(fd_handle h, int mode) {
   if (!h || (mode != 0 && mode != 1)) return fail(FD_EINVAL, "fd_train_set_gemm: mode %d", mode);
   h->train_gemm = mode;

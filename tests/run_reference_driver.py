@@ -61,7 +61,51 @@ def main():
            "shapes": {k: list(v.shape) for k, v in out.items()},
            "ok": bool(err <= 2e-3 * scale and abs(bond - 3.8088) < 5e-3 and prior_err < 1e-4)}
     print(json.dumps(res))
-    return 0 if res["ok"] else 1
+    ok_inf = res["ok"]
+    # ---- training: the reference's own loss_fn (+ _self_conditioning) and update step on the overlay model ----------------------------
+    # Experiment.update_fn (experiments/train_se3_diffusion.py:320-326) is `loss, aux = self.loss_fn(feats); optimizer.zero_grad();
+    # loss.backward(); optimizer.step()` — run verbatim on a light object carrying the attributes loss_fn touches; compared with the gradient
+    # norms the unmodified reference model produced on the same batch (tests/golden/loss_b.npz).
+    import collections, random, types
+    from oracle import framediff_oracle as fo
+    g = dict(np.load(os.path.join(HERE, "golden", "loss_b.npz"), allow_pickle=False))
+    net2 = score_network.ScoreNetwork(mc, dif, precision="fp32")
+    net2.load_state_dict({k: torch.tensor(v) for k, v in fo.synthetic_weights(0).items()}, strict=True)
+    net2 = net2.to(device)
+    net2.eval()                       # the golden was produced on an eval-mode module with autograd recording (make_golden_loss.py)
+    exp_conf = dict(trans_loss_weight=1.0, rot_loss_weight=0.5, rot_loss_t_threshold=0.2, separate_rot_loss=True, trans_x0_threshold=1.0,
+                    coordinate_scaling=0.1, bb_atom_loss_weight=1.0, bb_atom_loss_t_filter=0.25, dist_mat_loss_weight=1.0, dist_mat_loss_t_filter=0.25,
+                    aux_loss_weight=0.25)
+
+    class _Exp:
+        pass
+
+    ex2 = _Exp()
+    ex2._model_conf = mc; ex2._diff_conf = dc; ex2._exp_conf = rh.to_attr(exp_conf)
+    ex2.model = ex2._model = net2; ex2.diffuser = ex2._diffuser = dif
+    ex2._aux_data_history = collections.deque(maxlen=4)
+    for name in ("loss_fn", "_self_conditioning", "_set_t_feats"):
+        setattr(ex2, name, types.MethodType(getattr(tsd.Experiment, name), ex2))
+    batch = {k[3:]: torch.as_tensor(v).to(device) for k, v in g.items() if k.startswith("in_") and k != "in_sc_ca_t"}
+    batch["sc_ca_t"] = torch.zeros_like(batch["rigids_t"][..., 4:])
+    opt = torch.optim.Adam(net2.parameters(), lr=1e-4)            # train_se3_diffusion.py:139-141
+    random.seed(1)                                                 # the golden's self-conditioning coin flip
+    loss, aux = ex2.loss_fn(batch)
+    opt.zero_grad(); loss.backward(); opt.step()
+    names, norms = [str(n) for n in g["grad_names"]], g["grad_norms"]
+    named = dict(net2.named_parameters())
+    worst, n_none = 0.0, 0
+    for n, rn in zip(names, norms):
+        gr = named[n].grad
+        if rn < 0:
+            n_none += int(gr is None)
+            continue
+        worst = max(worst, abs(float(gr.double().norm()) - rn) / (rn + 1e-6))
+    res2 = {"driver": "Experiment.loss_fn + loss.backward() + Adam step (unmodified reference) on the overlay ScoreNetwork", "loss": float(loss),
+            "reference_loss_with_autograd_semantics": None, "worst_grad_norm_rel_err_vs_reference": worst, "params_with_grad_none": n_none,
+            "ok": bool(worst < 2e-3 and n_none == 10 and np.isfinite(float(loss)))}
+    print(json.dumps(res2))
+    return 0 if (ok_inf and res2["ok"]) else 1
 
 
 if __name__ == "__main__":

@@ -197,3 +197,24 @@ def test_unmodified_reference_driver_through_overlay():
                        text=True, timeout=1200)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
     assert json.loads(r.stdout.strip().splitlines()[-1])["ok"]
+
+
+def test_workspace_query_matches_allocations():
+    """SURVEY §8(b) workspace query: fd_workspace_bytes vs what the handle actually allocated (inference workspace in both modes, loop
+    buffers, training tape), within 3 %."""
+    from gpu_common import engine
+    from se3_diffusion_b200.synthetic import init_feats, random_frames
+    B, N = 3, 72
+    for prec in ("fp32", "bf16x3"):
+        e = engine(prec)
+        e.forward(init_feats(random_frames(B, N, seed=2), t=0.4))
+        est, act = e.lib.fd_workspace_bytes(e._h, 0, B, N, 0, 0), e.lib.fd_debug_alloc_bytes(e._h, 0)
+        assert act > 0 and abs(est - act) <= 0.03 * act, (prec, est, act)
+    e.sample(B, N, num_t=7, aux_traj=True)
+    est, act = e.lib.fd_workspace_bytes(e._h, 1, B, N, 7, 1), e.lib.fd_debug_alloc_bytes(e._h, 1)
+    assert act > 0 and abs(est - act) <= 0.05 * act + 65536, ("loop", est, act)
+    e2, g, batch, flat, grads = _setup("b")
+    e2.train_forward({k: batch[k] for k in FEAT_KEYS})
+    Bt, Nt = batch["res_mask"].shape
+    est, act = e2.lib.fd_workspace_bytes(e2._h, 2, Bt, Nt, 0, 0), e2.lib.fd_debug_alloc_bytes(e2._h, 2)
+    assert act > 0 and abs(est - act) <= 0.03 * act, ("tape", est, act)
