@@ -100,7 +100,7 @@ def main():
         if rn < 0:
             n_none += int(gr is None)
             continue
-        worst = max(worst, abs(float(gr.double().norm()) - rn) / (rn + 1e-6))
+        worst = max(worst, max(abs(float(gr.double().norm()) - rn) - 1e-6, 0.0) / rn)     # 1e-6 absolute floor: linear_b.bias is 0 analytically
     res2 = {"driver": "Experiment.loss_fn + loss.backward() + Adam step (unmodified reference) on the overlay ScoreNetwork", "loss": float(loss),
             "reference_loss_with_autograd_semantics": None, "worst_grad_norm_rel_err_vs_reference": worst, "params_with_grad_none": n_none,
             "ok": bool(worst < 2e-3 and n_none == 10 and np.isfinite(float(loss)))}

@@ -441,7 +441,8 @@ def test_diffuser_api_score_on_gpu(eng):
     ok = om <= 3.5 * sig
     assert ok.sum() > 0.3 * ok.size
     assert_close(np.asarray(rs)[ok], g["score_rot"][ok], 0, norm_rel=1e-4, name="score rot (well-conditioned)")
-    assert np.abs(np.asarray(rs)[~ok] - g["score_rot"][~ok]).max() <= 2e-2 * np.abs(g["score_rot"][ok]).max()
+    if (~ok).any():
+        assert np.abs(np.asarray(rs)[~ok] - g["score_rot"][~ok]).max() <= 2e-2 * np.abs(g["score_rot"][ok]).max()
 
 
 # ---- tensor-core (tcgen05) precisions ---------------------------------------------------------------------------------------
