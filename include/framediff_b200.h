@@ -82,6 +82,9 @@ typedef struct {
   const int32_t* seq_idx;       /* [B,N] 1-based residue index, 0 on padding */
   const float* sc_ca_t;         /* [B,N,3] self-conditioning CA (Å) */
   const float* gt_psi;          /* [B,N,2] torsion_angles_sin_cos[..., 2, :] (used where fixed_mask = 1); may be NULL */
+  const double* cached_score_rows; /* use_cached_score=True (so3_diffuser.py:291-298): [B,1000] fp64, row b = _score_norms[sigma_idx(t[b])]
+                                   (fd_igso3_tables_host builds them); the head then does the reference's bucketize + gather instead of
+                                   evaluating the series.  NULL (the shipped default) = series.  Inference only. */
 } fd_forward_in;
 
 typedef struct {

@@ -10,7 +10,7 @@ c_f32p, c_f64p, c_i32p, c_voidp = C.POINTER(C.c_float), C.POINTER(C.c_double), C
 
 class ForwardIn(C.Structure):
     _fields_ = [("rigids_t", c_voidp), ("t", c_voidp), ("t_is_f32", C.c_int), ("sigma", c_voidp), ("res_mask", c_voidp),
-                ("fixed_mask", c_voidp), ("seq_idx", c_voidp), ("sc_ca_t", c_voidp), ("gt_psi", c_voidp)]
+                ("fixed_mask", c_voidp), ("seq_idx", c_voidp), ("sc_ca_t", c_voidp), ("gt_psi", c_voidp), ("cached_score_rows", c_voidp)]
 
 
 class LossIn(C.Structure):

@@ -585,7 +585,7 @@ struct Fwd {
 static int forward_impl(fd_context* h, int B, int N, const float* rigids_t, const double* t_dev, int t_is_f32,
                         const double* sigma_dev, const float* res_mask, const float* fixed_mask, const int* seq_idx,
                         const float* sc_ca, const float* gt_psi, const fd_forward_out* out, float* sc_ca_out,
-                        cudaStream_t st) {
+                        cudaStream_t st, const double* cached_rows = nullptr) {
   CKI(ensure_ws(h, B, N));
   Workspace& w = h->ws;
   const Weights& W = h->W;
@@ -814,7 +814,7 @@ static int forward_impl(fd_context* h, int B, int N, const float* rigids_t, cons
     HeadArgs a;
     a.tors_s = w.tors; a.Wf = W.torf.w; a.bf = W.torf.b; a.quat = w.quat; a.trans = w.trans; a.rigids_t = rigids_t;
     a.t = t_dev; a.t_is_f32 = t_is_f32; a.sigma = sigma_dev; a.sigma_grid = h->d_sigma_grid;
-    a.res_mask = res_mask; a.fixed_mask = fixed_mask; a.gt_psi = gt_psi;
+    a.res_mask = res_mask; a.fixed_mask = fixed_mask; a.gt_psi = gt_psi; a.cached_rows = cached_rows; a.omega_grid = h->d_omega;
     a.rot_score = out->rot_score; a.trans_score = out->trans_score; a.psi = out->psi; a.rigids = out->rigids;
     a.atom37 = out->atom37; a.atom14 = out->atom14; a.sc_ca = sc_ca_out; a.rows = R; a.N = N;
     score_head_kernel<<<(unsigned)((R + 7) / 8), 256, 0, st>>>(a);
@@ -836,7 +836,7 @@ extern "C" int fd_forward(fd_handle h, int B, int N, const fd_forward_in* in, co
   DevGuard dev_guard(h->device);
   cudaStream_t st = (cudaStream_t)stream;
   const int rc = forward_impl(h, B, N, in->rigids_t, in->t, in->t_is_f32, in->sigma, in->res_mask, in->fixed_mask, in->seq_idx, in->sc_ca_t,
-                              in->gt_psi, out, nullptr, st);
+                              in->gt_psi, out, nullptr, st, in->cached_score_rows);
   if (rc == FD_OK && st != h->stream) { CK(cudaEventRecord(h->ev_fwd, st)); h->fwd_pending = true; }
   return rc;
 }
@@ -1377,6 +1377,7 @@ extern "C" int fd_train_forward(fd_handle h, int B, int N, const fd_forward_in* 
   if (!in->rigids_t || !in->t || !in->res_mask || !in->fixed_mask || !in->seq_idx || !in->sc_ca_t)
     return fail(FD_EINVAL, "fd_train_forward: a required input pointer is NULL");
   if (!out->rot_score || !out->trans_score || !out->psi || !out->rigids) return fail(FD_EINVAL, "fd_train_forward: a required output pointer is NULL");
+  if (in->cached_score_rows) return fail(FD_EINVAL, "fd_train_forward: use_cached_score is an inference-only lookup (piecewise constant in the angle)");
   DevGuard dev_guard(h->device);
   return train_forward_impl(h, h->train, B, N, in, out, (cudaStream_t)stream);
 }

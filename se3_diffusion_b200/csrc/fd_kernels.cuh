@@ -823,6 +823,8 @@ struct HeadArgs {
   const double* t; int t_is_f32; const double* sigma;        // per sample; sigma may be null -> quantise on device
   const double* sigma_grid;
   const float* res_mask; const float* fixed_mask; const float* gt_psi;  // gt_psi may be null
+  const double* cached_rows;       // use_cached_score (so3_diffuser.py:291-298): [B, 1000] rows of _score_norms at each sample's sigma index, or null
+  const double* omega_grid;        // discrete_omega [1000]
   double* rot_score; double* trans_score; float* psi; float* rigids; float* atom37; float* atom14;
   // optional secondary outputs for the sampling loop
   float* sc_ca;                                              // [rows,3] predicted CA (Å) -> next step's self-conditioning
@@ -876,7 +878,16 @@ __global__ void __launch_bounds__(256) score_head_kernel(const HeadArgs a) {
   }
   const double tt = a.t[b];
   const double sig = a.sigma ? a.sigma[b] : quantise_sigma(tt, a.sigma_grid);
-  const double sscal = igso3_score_scalar(omega, sig, lane);
+  double sscal;
+  if (a.cached_rows) {
+    // torch.bucketize(omega, discrete_omega[:-1]) (right = False): number of the first 999 grid points strictly below omega; then a gather
+    int lo = 0, hi = SO3_NOMEGA - 1;
+    const double om = (double)omega;
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (a.omega_grid[mid] < om) lo = mid + 1; else hi = mid; }
+    sscal = a.cached_rows[(long long)b * SO3_NOMEGA + lo];
+  } else {
+    sscal = igso3_score_scalar(omega, sig, lane);
+  }
   // --- translation score: -(x_t·0.1 − e^{−β̄/2}·x̂0·0.1) / (1 − e^{−β̄}) ----------------------------------------------
   if (lane < 3) {
     a.rot_score[row * 3 + lane] = sscal * (double)rv[lane] / (double)(omega + 1e-6f) * (double)m;

@@ -358,7 +358,7 @@ static int train_forward_impl(fd_context* h, fd_train_state* S, int B, int N, co
     HeadArgs a;
     a.tors_s = T.tors; a.Wf = f.w(tp + "linear_final.weight"); a.bf = f.w(tp + "linear_final.bias"); a.quat = T.quat_fin; a.trans = T.trans_fin;
     a.rigids_t = in->rigids_t; a.t = in->t; a.t_is_f32 = in->t_is_f32; a.sigma = nullptr; a.sigma_grid = h->d_sigma_grid;
-    a.res_mask = res_mask; a.fixed_mask = in->fixed_mask; a.gt_psi = in->gt_psi;
+    a.res_mask = res_mask; a.fixed_mask = in->fixed_mask; a.gt_psi = in->gt_psi; a.cached_rows = nullptr; a.omega_grid = h->d_omega;
     a.rot_score = out->rot_score; a.trans_score = out->trans_score; a.psi = out->psi; a.rigids = out->rigids; a.atom37 = out->atom37;
     a.atom14 = out->atom14; a.sc_ca = nullptr; a.rows = R; a.N = N;
     score_head_kernel<<<(unsigned)((R + 7) / 8), 256, 0, st>>>(a);

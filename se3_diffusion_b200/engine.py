@@ -51,6 +51,7 @@ class FrameDiffEngine:
         self.set_precision(precision)
         self._weights_version = None
         self.validate_t = False
+        self.use_cached_score = False   # SO3Diffuser.use_cached_score (config/base.yaml: False): table lookup instead of the IGSO(3) series
         self.last_gpu_ms = None
 
     def __del__(self):
@@ -122,8 +123,23 @@ class FrameDiffEngine:
         if want_atoms:
             out["atom37"] = torch.empty(B, N, 37, 3, device=dev, dtype=torch.float32)
             out["atom14"] = torch.empty(B, N, 14, 3, device=dev, dtype=torch.float32)
+        rows = None
+        if self.use_cached_score:
+            # so3_diffuser.py:291-298: rows of the precomputed _score_norms table at each sample's sigma index (t goes to the host, as in the
+            # reference's `self.t_to_idx(du.move_to_np(t))`); rows are built on the GPU once per index and kept on the device
+            tn = t64.cpu().numpy()
+            sig = np.log(tn * np.exp(1.5) + (1 - tn) * np.exp(0.1))
+            grid = np.log(np.linspace(0.0, 1.0, 1000) * np.exp(1.5) + (1 - np.linspace(0.0, 1.0, 1000)) * np.exp(0.1))
+            idx = np.digitize(sig, grid) - 1
+            cache = self.__dict__.setdefault("_score_rows", {})
+            miss = sorted({int(i) for i in idx if int(i) not in cache})
+            if miss:
+                tab = self.igso3_tables(miss)["score_norms"]
+                for k, i in enumerate(miss):
+                    cache[i] = torch.tensor(tab[k], device=dev)
+            rows = torch.stack([cache[int(i)] for i in idx]).contiguous()
         fin = ForwardIn(_ptr(rigids_t), _ptr(t64), t_is_f32, None, _ptr(res_mask), _ptr(fixed_mask), _ptr(seq_idx), _ptr(sc_ca),
-                        _ptr(gt_psi))
+                        _ptr(gt_psi), _ptr(rows))
         fout = ForwardOut(_ptr(out["rot_score"]), _ptr(out["trans_score"]), _ptr(out["psi"]), _ptr(out["rigids"]),
                           _ptr(out.get("atom37")), _ptr(out.get("atom14")))
         stream = torch.cuda.current_stream(dev)
@@ -134,7 +150,7 @@ class FrameDiffEngine:
             out["trans_score"] = out["trans_score"].to(torch.float32)
         if tors is not None and torch.as_tensor(tors).dtype == torch.float64:
             out["psi"] = out["psi"].to(torch.float64)
-        self._keep = (rigids_t, t64, res_mask, fixed_mask, seq_idx, sc_ca, gt_psi)
+        self._keep = (rigids_t, t64, res_mask, fixed_mask, seq_idx, sc_ca, gt_psi, rows)
         return out
 
     # ---- SE3Diffuser pieces ----------------------------------------------------------------------------------------------
@@ -206,6 +222,9 @@ class FrameDiffEngine:
         Returns the reference's inference_fn dict (prot_traj, and rigid_traj/trans_traj/rigid_0_traj/psi_pred when
         aux_traj) plus 'gpu_ms' and 'kernel_launches'.  Without aux_traj, prot_traj has a single frame (the sample).
         """
+        if self.use_cached_score:
+            raise ValueError("the device-resident loop evaluates the IGSO(3) series (use_cached_score=False, the shipped default); the table "
+                             "look-up is available through ScoreNetwork.forward, i.e. the unchanged driver loop")
         cfg = SampleCfg(B, N, num_t, min_t, noise_scale, int(center), int(self_condition), int(aux_traj), seed, first_sample,
                         int(use_graph))
         keep = []
@@ -473,7 +492,7 @@ def _train_forward(self, feats: Dict[str, torch.Tensor]) -> Dict[str, torch.Tens
            "psi": torch.empty(B, N, 2, device=dev, dtype=torch.float32), "rigids": torch.empty(B, N, 7, device=dev, dtype=torch.float32),
            "atom37": torch.empty(B, N, 37, 3, device=dev, dtype=torch.float32), "atom14": torch.empty(B, N, 14, 3, device=dev, dtype=torch.float32)}
     fin = ForwardIn(_ptr(keep["rigids_t"]), _ptr(keep["t"]), t_is_f32, None, _ptr(keep["res_mask"]), _ptr(keep["fixed_mask"]), _ptr(keep["seq_idx"]),
-                    _ptr(keep["sc_ca"]), _ptr(keep["gt_psi"]))
+                    _ptr(keep["sc_ca"]), _ptr(keep["gt_psi"]), None)
     fout = ForwardOut(*[_ptr(out[k]) for k in ("rot_score", "trans_score", "psi", "rigids", "atom37", "atom14")])
     st = torch.cuda.current_stream(dev)
     check(self.lib.fd_train_forward(self._h, B, N, C.byref(fin), C.byref(fout), C.c_void_p(st.cuda_stream)))

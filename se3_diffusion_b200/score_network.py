@@ -256,6 +256,9 @@ class ScoreNetwork(nn.Module):
             raise RuntimeError("ScoreNetwork (B200) has no CPU path: move the model and its inputs to a CUDA device")
         needs_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
         if needs_grad or self.training:
+            if getattr(getattr(self.diffuser, "_so3_diffuser", None), "use_cached_score", False):
+                raise ValueError("use_cached_score=True is an inference-only table look-up on the B200 path (piecewise constant in the angle); "
+                                 "train with the shipped default use_cached_score=False")
             # torch's TransformerEncoder leaves its fused inference path whenever the module is in train() mode or autograd records; the
             # training-mode CUDA forward has those semantics (float key-padding mask added to the logits)
             self._flatten_parameters(torch.device(dev))

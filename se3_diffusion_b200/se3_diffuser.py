@@ -50,8 +50,6 @@ class _SO3Facade:
         self.schedule, self.use_cached_score = conf.schedule, conf.use_cached_score
         if (conf.min_sigma, conf.max_sigma, conf.num_sigma, conf.num_omega, conf.schedule) != (0.1, 1.5, 1000, 1000, "logarithmic"):
             raise ValueError("the B200 kernels are compiled for the shipped IGSO(3) configuration (config/base.yaml:35-43)")
-        if conf.use_cached_score:
-            raise ValueError("use_cached_score=True is not built into the B200 path (base.yaml default is False)")
 
     def sigma(self, t):
         t = np.asarray(t, dtype=np.float64)
@@ -109,11 +107,13 @@ class SE3Diffuser:
     def _engine(self) -> FrameDiffEngine:
         if self._eng is None:
             self._eng = FrameDiffEngine(self._device if self._device is not None else torch.cuda.current_device())
+            self._eng.use_cached_score = bool(self._so3_diffuser.use_cached_score)
         return self._eng
 
     def bind_engine(self, engine: FrameDiffEngine):
         """Share the ScoreNetwork's engine (one handle per process and device)."""
         self._eng = engine
+        engine.use_cached_score = bool(self._so3_diffuser.use_cached_score)     # the network's rotation-score head follows the diffuser's switch
 
     # ---- noising (training data) -------------------------------------------------------------------------------------
     def forward_marginal(self, rigids_0, t: float, diffuse_mask: np.ndarray = None, as_tensor_7: bool = True):
@@ -166,6 +166,15 @@ class SE3Diffuser:
         sig = self._so3_diffuser.sigma(t_np)
         grid = self._so3_diffuser.sigma(np.linspace(0.0, 1.0, 1000))
         sig_q = grid[np.digitize(sig, grid) - 1]
+        if self._so3_diffuser.use_cached_score:
+            # so3_diffuser.py:291-298: bucketize the angle on the omega grid and gather from the precomputed score-norm rows (built on the GPU)
+            idx = np.digitize(sig, grid) - 1
+            rows = torch.tensor(self._engine().igso3_tables([int(i) for i in idx])["score_norms"]).to(rotvec.device)     # [B,1000]
+            omega = torch.linalg.norm(rotvec, dim=-1) + 1e-6
+            om_grid = torch.tensor(np.linspace(0, np.pi, 1001)[1:-1]).to(rotvec.device)
+            oi = torch.bucketize(omega, om_grid)
+            sc = torch.gather(rows, 1, oi.reshape(rows.shape[0], -1)).reshape(omega.shape)
+            return sc[..., None] * rotvec / (omega[..., None] + 1e-6)
         sigma = torch.tensor(sig_q).reshape(-1, *([1] * (rotvec.ndim - 2))).expand(rotvec.shape[:-1])
         return self._engine().igso3_score(rotvec, sigma).to(rotvec.device)
 

@@ -706,3 +706,28 @@ def test_ca_metrics_vs_oracle_and_reference_golden(eng):
         dev, valid = fo.ca_ca_distance(ca[k, :nv[k]]); ncl, pcl = fo.ca_ca_clashes(ca[k, :nv[k]])
         assert_close(got[k], np.array([dev, valid, ncl, pcl], dtype=np.float64), 1e-6, atol=1e-9, name=f"metrics {k} vs oracle")
         assert got[k][2] == g[f"ref_{k}"][2]                                                          # clash COUNT: integer, bit-exact
+
+
+def test_forward_use_cached_score_lookup(eng):
+    """SO3Diffuser.use_cached_score=True (so3_diffuser.py:291-298): the head's bucketize + gather from the precomputed score-norm rows vs
+    the oracle's restatement of that branch.  The look-up is a step function of the angle, so an angle within rounding of a grid point may
+    land in the neighbouring bucket: all but a handful of residues must agree to 1e-6, the rest to the neighbouring table entry."""
+    np.random.seed(31)
+    B, N = 2, 80
+    r7 = torch.stack([fo.sample_ref(N) for _ in range(B)])
+    f = fo.init_feats(r7)
+    f["t"] = torch.tensor([0.77, 0.36], dtype=torch.float64)
+    with torch.no_grad():
+        ref = fo.score_network_forward(fo.as_torch_weights(fo.synthetic_weights(0)), f, use_cached_score=True)
+    eng.use_cached_score = True
+    try:
+        out = eng.forward(f)
+        with pytest.raises(ValueError):
+            eng.sample(1, 16, num_t=3)
+    finally:
+        eng.use_cached_score = False
+    a, b = out["rot_score"].cpu().numpy(), ref["rot_score"].numpy()
+    rel = np.abs(a - b).max(-1) / np.maximum(np.abs(b).max(-1), 1e-30)
+    assert (rel < 1e-4).mean() > 0.97, f"only {(rel < 1e-4).mean():.3f} of the residues agree"
+    assert rel.max() < 0.2                      # a neighbouring bucket, not garbage
+    assert_close(out["trans_score"].cpu().numpy(), ref["trans_score"].numpy(), 0, norm_rel=1e-4, name="trans_score")
