@@ -117,6 +117,7 @@ struct fd_context {
     double noise_scale = 0; uint64_t seed = 0; long long first_sample = 0;
     const void *ws_base = nullptr, *lb_base = nullptr, *warena = nullptr;
   } gc;
+  double* d_loss_acc = nullptr;            // [4096][10] partial sums of the loss kernels
   int train_gemm = 0;                      // training-path GEMMs: 0 = fp32 CUDA cores, 1 = split-bf16 mma.sync tensor cores (fd_mm3.cuh)
   struct fd_train_state* train = nullptr;   // training step state (bound arenas + tape), fd_train_host.cuh
   cudaEvent_t ev_fwd = nullptr;      // recorded after fd_forward on the caller's stream; the sampling stream waits on it (shared workspace)
@@ -263,6 +264,7 @@ extern "C" int fd_destroy(fd_handle h) {
   cudaFree(h->d_sigma_grid); cudaFree(h->d_cdf_t1); cudaFree(h->d_omega); cudaFree(h->d_sched1);
   if (h->d_t_tmp) cudaFree(h->d_t_tmp);
   free_train(h);
+  if (h->d_loss_acc) cudaFree(h->d_loss_acc);
   if (h->ev_fwd) cudaEventDestroy(h->ev_fwd);
   cudaStreamDestroy(h->stream);
   delete h;
@@ -1466,8 +1468,21 @@ extern "C" int fd_loss_backward(fd_handle h, int B, int N, const fd_loss_in* in,
   a.separate_rot_loss = cfg->separate_rot_loss; a.diffuse_trans = cfg->diffuse_trans; a.diffuse_rot = cfg->diffuse_rot;
   a.inv_nvalid = 1.0 / ((double)nvalid + 1e-10);
   a.d_rot = out->d_rot_score; a.d_trans = out->d_trans_score; a.d_rigids = out->d_rigids; a.d_atom37 = out->d_atom37; a.N = N;
-  loss_backward_kernel<<<B, 256, smem, st>>>(a);
-  CK(cudaGetLastError());
+  {
+    const size_t smem2 = (size_t)32 * N * sizeof(float);
+    if (smem2 > 48 * 1024) {
+      CK(cudaFuncSetAttribute(loss_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+      CK(cudaFuncSetAttribute(loss_bwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+    }
+    if (!h->d_loss_acc) CK(cudaMalloc(&h->d_loss_acc, 4096 * 10 * sizeof(double)));
+    if (B > 4096) return fail(FD_EINVAL, "fd_loss_backward: B = %d too large", B);
+    CK(cudaMemsetAsync(h->d_loss_acc, 0, (size_t)B * 3 * sizeof(double), st));
+    const dim3 grid(B, (N + LOSS_RES - 1) / LOSS_RES);
+    loss_count_kernel<<<grid, 256, smem2, st>>>(a, h->d_loss_acc);
+    CK(cudaGetLastError());
+    loss_bwd2_kernel<<<grid, 256, smem2, st>>>(a, h->d_loss_acc);
+    CK(cudaGetLastError());
+  }
   return FD_OK;
 }
 extern "C" int fd_adam_step(fd_handle h, float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, double lr, double beta1,
@@ -1545,8 +1560,18 @@ extern "C" int fd_loss_forward(fd_handle h, int B, int N, const fd_loss_in* in, 
   a.dist_mat_loss_t_filter = cfg->dist_mat_loss_t_filter; a.aux_loss_weight = cfg->aux_loss_weight;
   a.separate_rot_loss = cfg->separate_rot_loss; a.diffuse_trans = cfg->diffuse_trans; a.diffuse_rot = cfg->diffuse_rot;
   a.terms = terms_dev; a.N = N;
-  loss_forward_kernel<<<B, 256, smem, static_cast<cudaStream_t>(stream)>>>(a);
-  CK(cudaGetLastError());
+  {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const size_t smem2 = (size_t)32 * N * sizeof(float);
+    if (smem2 > 48 * 1024) CK(cudaFuncSetAttribute(loss_fwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+    if (!h->d_loss_acc) CK(cudaMalloc(&h->d_loss_acc, 4096 * 10 * sizeof(double)));
+    if (B > 4096) return fail(FD_EINVAL, "fd_loss_forward: B = %d too large", B);
+    CK(cudaMemsetAsync(h->d_loss_acc, 0, (size_t)B * 10 * sizeof(double), st));
+    loss_fwd2_kernel<<<dim3(B, (N + LOSS_RES - 1) / LOSS_RES), 256, smem2, st>>>(a, h->d_loss_acc);
+    CK(cudaGetLastError());
+    loss_finalize_kernel<<<(B + 127) / 128, 128, 0, st>>>(a, h->d_loss_acc, B);
+    CK(cudaGetLastError());
+  }
   return FD_OK;
 }
 

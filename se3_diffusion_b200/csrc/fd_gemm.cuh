@@ -27,6 +27,8 @@ struct GemmArgs {
   const float* relumask = nullptr; int ldm = 0;   // v = relumask[m][n] > 0 ? v : 0 (backward of a ReLU whose OUTPUT is relumask), applied last
   int splits = 1;                       // split-K: blockIdx.z = batch * splits + split, partial sums combined with atomicAdd (needs atomic = 1)
   int atomic = 0;                       // C[m][n] += alpha*acc through atomicAdd (gradient accumulation); bias/rowadd/relu/residual ignored
+  float* colsum_out = nullptr;          // weight-gradient form only (A = dy[k][m]): colsum_out[m] += sum_k A[k][m] — the bias gradient, taken from the
+                                        // A tiles the n-tile-0 CTAs stream anyway (mm3_kernel; the CUDA-core kernel ignores it)
 };
 
 // A_KMAJOR = true : A is A[m][k] (row-major activations, K contiguous)

@@ -21,8 +21,12 @@ constexpr int MM3_PLANE = 128 * MM3_KSTRIDE;                 // 10240 B (>= 32 *
 constexpr int MM3_STAGE = 4 * MM3_PLANE;                     // A hi | A lo | B hi | B lo
 constexpr size_t MM3_SMEM = 2 * MM3_STAGE;
 
-template <bool A_KMAJOR, bool B_KMAJOR>
-__global__ void __launch_bounds__(256) mm3_kernel(const GemmArgs g) {
+// MT = m16 tiles per warp: 4 -> 8 warps (2 x 4, 64x32 per warp, 256 threads); 2 -> 16 warps (4 x 4, 32x32 per warp, 512 threads: more warps in
+// flight per SM, fewer registers per thread)
+template <bool A_KMAJOR, bool B_KMAJOR, int MT = 4>
+__global__ void __launch_bounds__(1024 / MT) mm3_kernel(const GemmArgs g) {
+  constexpr int NTHR = 1024 / MT;          // 256 or 512
+  constexpr int NLD = 1024 / NTHR;         // float4 loads per thread and operand: 4 or 2
   extern __shared__ __align__(128) uint8_t mm3_smem[];
   const uint32_t sbase = smem_u32(mm3_smem);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -41,7 +45,13 @@ __global__ void __launch_bounds__(256) mm3_kernel(const GemmArgs g) {
     if (kbeg >= K) return;
   }
 
-  float4 ra[4], rb[4];
+  // bias gradient riding on the weight gradient: column sums of the A tiles (threads keep their (k row, m quad) slots across k-steps)
+  const bool do_colsum = !A_KMAJOR && g.colsum_out != nullptr && blockIdx.x == 0;
+  float4 csum[NLD];
+#pragma unroll
+  for (int it = 0; it < NLD; ++it) csum[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+  float4 ra[NLD], rb[NLD];
   // ---- global -> registers (fp32, zero-filled outside the problem) ----
   auto load_one = [&](const float* __restrict__ P, int ld, bool kmajor, int vec, int r0, int R, int k0, int idx) -> float4 {
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -76,9 +86,9 @@ __global__ void __launch_bounds__(256) mm3_kernel(const GemmArgs g) {
   };
   auto load_tiles = [&](int k0) {
 #pragma unroll
-    for (int it = 0; it < 4; ++it) {
-      ra[it] = load_one(A, g.lda, A_KMAJOR, g.vecA, m0, M, k0, tid + it * 256);
-      rb[it] = load_one(B, g.ldb, B_KMAJOR, g.vecB, n0, N, k0, tid + it * 256);
+    for (int it = 0; it < NLD; ++it) {
+      ra[it] = load_one(A, g.lda, A_KMAJOR, g.vecA, m0, M, k0, tid + it * NTHR);
+      rb[it] = load_one(B, g.ldb, B_KMAJOR, g.vecB, n0, N, k0, tid + it * NTHR);
     }
   };
   // ---- registers -> shared (bf16 hi / lo) ----
@@ -94,20 +104,24 @@ __global__ void __launch_bounds__(256) mm3_kernel(const GemmArgs g) {
   };
   auto store_tiles = [&](int buf) {
     const uint32_t st = sbase + buf * MM3_STAGE;
+    if (do_colsum) {
 #pragma unroll
-    for (int it = 0; it < 4; ++it) {
-      store_one(st, st + MM3_PLANE, A_KMAJOR, tid + it * 256, ra[it]);
-      store_one(st + 2 * MM3_PLANE, st + 3 * MM3_PLANE, B_KMAJOR, tid + it * 256, rb[it]);
+      for (int it = 0; it < NLD; ++it) { csum[it].x += ra[it].x; csum[it].y += ra[it].y; csum[it].z += ra[it].z; csum[it].w += ra[it].w; }
+    }
+#pragma unroll
+    for (int it = 0; it < NLD; ++it) {
+      store_one(st, st + MM3_PLANE, A_KMAJOR, tid + it * NTHR, ra[it]);
+      store_one(st + 2 * MM3_PLANE, st + 3 * MM3_PLANE, B_KMAJOR, tid + it * NTHR, rb[it]);
     }
   };
 
-  float acc[4][4][4];
+  float acc[MT][4][4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < MT; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) { acc[i][j][0] = 0.f; acc[i][j][1] = 0.f; acc[i][j][2] = 0.f; acc[i][j][3] = 0.f; }
 
-  const int wm = (warp >> 2) * 64, wn = (warp & 3) * 32;       // warp tile origin inside the CTA tile
+  const int wm = (warp >> 2) * (16 * MT), wn = (warp & 3) * 32;       // warp tile origin inside the CTA tile
   const int mi = lane >> 3, lr = lane & 7;
 
   const int nk = (K - kbeg + MM3_BK - 1) / MM3_BK;
@@ -137,7 +151,7 @@ __global__ void __launch_bounds__(256) mm3_kernel(const GemmArgs g) {
         bl[2 * np][0] = s[0]; bl[2 * np][1] = s[1]; bl[2 * np + 1][0] = s[2]; bl[2 * np + 1][1] = s[3];
       }
 #pragma unroll
-      for (int mt = 0; mt < 4; ++mt) {
+      for (int mt = 0; mt < MT; ++mt) {
         uint32_t ah[4], al[4];
         if (A_KMAJOR) {                          // smem [m][k]: matrices (m 0-7,k lo) (m 8-15,k lo) (m 0-7,k hi) (m 8-15,k hi)
           const uint32_t off = (uint32_t)((wm + mt * 16 + (mi & 1) * 8 + lr) * MM3_KSTRIDE + (ks * 2 + (mi >> 1)) * 16);
@@ -160,11 +174,29 @@ __global__ void __launch_bounds__(256) mm3_kernel(const GemmArgs g) {
     }
   }
 
+  if (do_colsum) {
+    // slot it of thread tid covered tile rows k = (tid + 256 it) >> 5 and columns m0 + ((tid + 256 it) & 31) * 4 + {0..3}: (tid & 31) is the
+    // same for all four slots, so a thread's four partial sums belong to the same 4 columns; 8 threads (tid >> 5) share them
+    __syncthreads();
+    float* red = reinterpret_cast<float*>(mm3_smem);            // [NTHR/32][128]
+    float4 t4 = csum[0];
+#pragma unroll
+    for (int it = 1; it < NLD; ++it) { t4.x += csum[it].x; t4.y += csum[it].y; t4.z += csum[it].z; t4.w += csum[it].w; }
+    *reinterpret_cast<float4*>(red + (tid >> 5) * 128 + (tid & 31) * 4) = t4;
+    __syncthreads();
+    if (tid < 128 && m0 + tid < M) {
+      float sacc = 0.f;
+#pragma unroll
+      for (int w8 = 0; w8 < NTHR / 32; ++w8) sacc += red[w8 * 128 + tid];
+      atomicAdd(g.colsum_out + m0 + tid, sacc);
+    }
+  }
+
   // ---- epilogue (same order as gemm_kernel): +bias, +rowadd, +C, relu, *rowmask, +residual, relu-mask; or atomicAdd ----
   const float* R = g.residual ? g.residual + z0 * g.sR0 + z1 * g.sR1 : nullptr;
   const int gq = lane >> 2, tq = lane & 3;
 #pragma unroll
-  for (int mt = 0; mt < 4; ++mt) {
+  for (int mt = 0; mt < MT; ++mt) {
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
       const int m = m0 + wm + mt * 16 + gq + half * 8;
@@ -204,12 +236,17 @@ __global__ void __launch_bounds__(256) mm3_kernel(const GemmArgs g) {
 }
 
 static bool g_mm3_ready = false;
+static int g_mm3_mt = 2;          // FD_MM3_MT=4 selects the 8-warp variant (kept for A/B measurements)
 inline int mm3_init() {
   if (g_mm3_ready) return 0;
+  if (const char* e = getenv("FD_MM3_MT")) g_mm3_mt = atoi(e) == 4 ? 4 : 2;
   cudaError_t e = cudaSuccess;
-  e = cudaFuncSetAttribute(mm3_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MM3_SMEM); if (e != cudaSuccess) return -1;
-  e = cudaFuncSetAttribute(mm3_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MM3_SMEM); if (e != cudaSuccess) return -1;
-  e = cudaFuncSetAttribute(mm3_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MM3_SMEM); if (e != cudaSuccess) return -1;
+  e = cudaFuncSetAttribute(mm3_kernel<true, true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MM3_SMEM); if (e != cudaSuccess) return -1;
+  e = cudaFuncSetAttribute(mm3_kernel<true, false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MM3_SMEM); if (e != cudaSuccess) return -1;
+  e = cudaFuncSetAttribute(mm3_kernel<false, false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MM3_SMEM); if (e != cudaSuccess) return -1;
+  e = cudaFuncSetAttribute(mm3_kernel<true, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MM3_SMEM); if (e != cudaSuccess) return -1;
+  e = cudaFuncSetAttribute(mm3_kernel<true, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MM3_SMEM); if (e != cudaSuccess) return -1;
+  e = cudaFuncSetAttribute(mm3_kernel<false, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MM3_SMEM); if (e != cudaSuccess) return -1;
   g_mm3_ready = true;
   return 0;
 }
@@ -224,9 +261,15 @@ inline cudaError_t launch_gemm_mm3(GemmArgs g, bool b_kmajor, cudaStream_t st, b
   if (g.splits < 1) g.splits = 1;
   if (g.splits > 1 && !g.atomic) return cudaErrorInvalidValue;
   dim3 grid((g.N + MM3_BN - 1) / MM3_BN, (g.M + MM3_BM - 1) / MM3_BM, g.nb0 * g.nb1 * g.splits);
-  if (a_kmajor && b_kmajor) mm3_kernel<true, true><<<grid, 256, MM3_SMEM, st>>>(g);
-  else if (a_kmajor) mm3_kernel<true, false><<<grid, 256, MM3_SMEM, st>>>(g);
-  else mm3_kernel<false, false><<<grid, 256, MM3_SMEM, st>>>(g);
+  if (g_mm3_mt == 4) {
+    if (a_kmajor && b_kmajor) mm3_kernel<true, true, 4><<<grid, 256, MM3_SMEM, st>>>(g);
+    else if (a_kmajor) mm3_kernel<true, false, 4><<<grid, 256, MM3_SMEM, st>>>(g);
+    else mm3_kernel<false, false, 4><<<grid, 256, MM3_SMEM, st>>>(g);
+  } else {
+    if (a_kmajor && b_kmajor) mm3_kernel<true, true, 2><<<grid, 512, MM3_SMEM, st>>>(g);
+    else if (a_kmajor) mm3_kernel<true, false, 2><<<grid, 512, MM3_SMEM, st>>>(g);
+    else mm3_kernel<false, false, 2><<<grid, 512, MM3_SMEM, st>>>(g);
+  }
   return cudaGetLastError();
 }
 

@@ -1029,6 +1029,225 @@ __global__ void __launch_bounds__(256) loss_backward_kernel(const LossBwdArgs a)
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+// DSM loss, version 2: the same arithmetic as loss_forward_kernel / loss_backward_kernel spread over grid (B, slabs) — the
+// 5N x 5N pair loop of ONE CTA per example was 6 % of a training step at B = 8.  Every CTA stages the example's ground-truth and
+// predicted backbone atoms in shared memory (cheap, O(N)) and owns LOSS_RES residues: their per-residue terms and their 5*LOSS_RES
+// rows of the pair matrix.  Forward: partial sums -> atomicAdd(double) into acc[b][10], a second tiny kernel forms the terms.
+// Backward: the pair denominator comes from a counting launch; row p's gradient is sum_q (c_pq + c_qp)(x_p - x_q) — both ordered pairs
+// evaluated by the owner of p, so no atomics and no second writer.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int LOSS_RES = 16;
+struct LossStage {            // shared-memory staging of one example
+  float* gt5; float* pr5; float* fl; float* fr;   // [5N][3], [5N][3], [N] loss mask, [N] res mask
+};
+__device__ __forceinline__ LossStage loss_stage(float* lsm, int N, int b, const double* rigids_0, const float* gt_psi, const float* pred_atom37,
+                                                const float* res_mask, const float* fixed_mask) {
+  LossStage S{lsm, lsm + 15 * N, lsm + 30 * N, lsm + 31 * N};
+  const long long r0 = (long long)b * N;
+  for (int n = threadIdx.x; n < N; n += blockDim.x) {
+    float q[4], R[9], t3[3], a37[111];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) q[k] = (float)rigids_0[(r0 + n) * 7 + k];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) t3[k] = (float)rigids_0[(r0 + n) * 7 + 4 + k];
+    quat_to_rot(q, R);
+    backbone_atoms(R, t3, gt_psi[(r0 + n) * 2], gt_psi[(r0 + n) * 2 + 1], a37, nullptr);
+#pragma unroll
+    for (int k = 0; k < 15; ++k) { S.gt5[n * 15 + k] = a37[k]; S.pr5[n * 15 + k] = pred_atom37[(r0 + n) * 111 + k]; }
+    S.fl[n] = res_mask[r0 + n] * (1.f - fixed_mask[r0 + n]);
+    S.fr[n] = res_mask[r0 + n];
+  }
+  __syncthreads();
+  return S;
+}
+__device__ __forceinline__ bool atom_present(const float* g) { return (fabsf(g[0]) + fabsf(g[1]) + fabsf(g[2])) != 0.f; }
+
+// acc[b][0..9] = { mask, trans_score, trans_x0, axis, angle, rot, bb, bbm, pair sum, pair count }
+__global__ void __launch_bounds__(256) loss_fwd2_kernel(const LossArgs a, double* __restrict__ acc) {
+  extern __shared__ __align__(16) float lsm[];
+  __shared__ double red[8];
+  const int N = a.N, b = blockIdx.x, tid = threadIdx.x;
+  const LossStage S = loss_stage(lsm, N, b, a.rigids_0, a.gt_psi, a.pred_atom37, a.res_mask, a.fixed_mask);
+  const int n0 = blockIdx.y * LOSS_RES, n1 = min(N, n0 + LOSS_RES);
+  double v[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  for (int i = n0 + tid; i < n1; i += 256) {
+    const long long r = (long long)b * N + i;
+    const double dm = 1.0 - (double)a.fixed_mask[r], lm = (double)a.res_mask[r] * dm;
+    v[0] += lm;
+    double ga = 0.0, pa = 0.0, g[3], q[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const double pt = a.pred_trans[r * 3 + k] * dm, dt = a.gt_trans[r * 3 + k] - pt;
+      v[1] += dt * dt * lm;
+      const double x0 = a.rigids_0[r * 7 + 4 + k] * a.coordinate_scaling - (double)a.pred_rigids[r * 7 + 4 + k] * a.coordinate_scaling;
+      v[2] += x0 * x0 * lm;
+      g[k] = a.gt_rot[r * 3 + k]; q[k] = a.pred_rot[r * 3 + k] * dm;
+      ga += g[k] * g[k]; pa += q[k] * q[k];
+      const double dr = g[k] - q[k];
+      v[5] += dr * dr * lm;
+    }
+    ga = sqrt(ga); pa = sqrt(pa);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { const double d = g[k] / (ga + 1e-6) - q[k] / (pa + 1e-6); v[3] += d * d * lm; }
+    v[4] += (ga - pa) * (ga - pa) * lm;
+#pragma unroll
+    for (int at = 0; at < 5; ++at) {
+      const float* gp = S.gt5 + (i * 5 + at) * 3; const float* pp = S.pr5 + (i * 5 + at) * 3;
+      const double mk = atom_present(gp) ? 1.0 : 0.0;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) { const float df = pp[k] - gp[k]; v[6] += (double)(df * df) * mk * lm; }
+      v[7] += mk * lm;
+    }
+  }
+  // pair rows x of this slab (5 atoms per residue), all columns y
+  const int M = 5 * N, x0r = 5 * n0, x1r = 5 * n1;
+  for (long long pidx = tid; pidx < (long long)(x1r - x0r) * M; pidx += 256) {
+    const int x = x0r + (int)(pidx / M), y = (int)(pidx % M);
+    const float lmx = S.fl[x / 5], rmy = S.fr[y / 5];
+    const float gx = S.gt5[x * 3] - S.gt5[y * 3], gy = S.gt5[x * 3 + 1] - S.gt5[y * 3 + 1], gz = S.gt5[x * 3 + 2] - S.gt5[y * 3 + 2];
+    const float px = S.pr5[x * 3] - S.pr5[y * 3], py = S.pr5[x * 3 + 1] - S.pr5[y * 3 + 1], pz = S.pr5[x * 3 + 2] - S.pr5[y * 3 + 2];
+    const float gd = sqrtf(gx * gx + gy * gy + gz * gz) * lmx, pd = sqrtf(px * px + py * py + pz * pz) * lmx;
+    const double pm = (double)lmx * (double)rmy * (gd < 6.f ? 1.0 : 0.0);
+    const double dd = (double)gd - (double)pd;
+    v[8] += dd * dd * pm; v[9] += pm;
+  }
+#pragma unroll
+  for (int k = 0; k < 10; ++k) {
+    const double s = block_sum_f64_t(v[k], red);
+    if (tid == 0 && s != 0.0) atomicAdd(acc + (long long)b * 10 + k, s);
+  }
+}
+__global__ void loss_finalize_kernel(const LossArgs a, const double* __restrict__ acc, int B) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const double* s = acc + (long long)b * 10;
+  const double tb = a.t[b], denom = s[0] + 1e-10;
+  const double ts2 = a.trans_scaling[b] * a.trans_scaling[b], rs2 = a.rot_scaling[b] * a.rot_scaling[b];
+  double trans_loss = (tb > a.trans_x0_threshold ? (s[1] / ts2) / denom : 0.0) + (tb <= a.trans_x0_threshold ? s[2] / denom : 0.0);
+  trans_loss *= a.trans_loss_weight * (double)a.diffuse_trans;
+  double rot_loss;
+  if (a.separate_rot_loss) rot_loss = (s[4] / rs2) / denom * a.rot_loss_weight * (tb > a.rot_loss_t_threshold ? 1.0 : 0.0) + s[3] / denom;
+  else rot_loss = (s[5] / rs2) / denom * a.rot_loss_weight * (tb > a.rot_loss_t_threshold ? 1.0 : 0.0);
+  rot_loss *= (double)a.diffuse_rot;
+  const double bb_loss = s[6] / (s[7] + 1e-10) * a.bb_atom_loss_weight * (tb < a.bb_atom_loss_t_filter ? 1.0 : 0.0) * a.aux_loss_weight;
+  const double dm_loss = s[8] / (s[9] - (double)a.N) * a.dist_mat_loss_weight * (tb < a.dist_mat_loss_t_filter ? 1.0 : 0.0) * a.aux_loss_weight;
+  double* o = a.terms + (long long)b * 5;
+  o[0] = rot_loss; o[1] = trans_loss; o[2] = bb_loss; o[3] = dm_loss; o[4] = ((rot_loss + trans_loss) + bb_loss) + dm_loss;
+}
+
+// acc[b][0..2] = { loss-mask sum, backbone-atom mask sum, pair-mask sum }  (denominators of the backward)
+__global__ void __launch_bounds__(256) loss_count_kernel(const LossBwdArgs a, double* __restrict__ acc) {
+  extern __shared__ __align__(16) float lsm[];
+  __shared__ double red[8];
+  const int N = a.N, b = blockIdx.x, tid = threadIdx.x;
+  const LossStage S = loss_stage(lsm, N, b, a.rigids_0, a.gt_psi, a.pred_atom37, a.res_mask, a.fixed_mask);
+  const int n0 = blockIdx.y * LOSS_RES, n1 = min(N, n0 + LOSS_RES);
+  double v[3] = {0, 0, 0};
+  for (int i = n0 + tid; i < n1; i += 256) {
+    v[0] += (double)S.fl[i];
+#pragma unroll
+    for (int at = 0; at < 5; ++at) if (atom_present(S.gt5 + (i * 5 + at) * 3)) v[1] += (double)S.fl[i];
+  }
+  const int M = 5 * N, x0r = 5 * n0, x1r = 5 * n1;
+  for (long long pidx = tid; pidx < (long long)(x1r - x0r) * M; pidx += 256) {
+    const int x = x0r + (int)(pidx / M), y = (int)(pidx % M);
+    const float lmx = S.fl[x / 5];
+    const float gx = S.gt5[x * 3] - S.gt5[y * 3], gy = S.gt5[x * 3 + 1] - S.gt5[y * 3 + 1], gz = S.gt5[x * 3 + 2] - S.gt5[y * 3 + 2];
+    if (sqrtf(gx * gx + gy * gy + gz * gz) * lmx < 6.f) v[2] += (double)lmx * (double)S.fr[y / 5];
+  }
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const double s = block_sum_f64_t(v[k], red);
+    if (tid == 0 && s != 0.0) atomicAdd(acc + (long long)b * 3 + k, s);
+  }
+}
+__global__ void __launch_bounds__(256) loss_bwd2_kernel(const LossBwdArgs a, const double* __restrict__ acc) {
+  extern __shared__ __align__(16) float lsm[];
+  const int N = a.N, b = blockIdx.x, tid = threadIdx.x;
+  const LossStage S = loss_stage(lsm, N, b, a.rigids_0, a.gt_psi, a.pred_atom37, a.res_mask, a.fixed_mask);
+  const int n0 = blockIdx.y * LOSS_RES, n1 = min(N, n0 + LOSS_RES);
+  const double tt = a.t[b], ws = a.inv_nvalid;
+  const double denom = acc[(long long)b * 3] + 1e-10, bm_sum = acc[(long long)b * 3 + 1], pden = acc[(long long)b * 3 + 2] - (double)N;
+  const double hi_t = tt > a.trans_x0_threshold ? 1.0 : 0.0;
+  const double wa = a.rot_loss_weight * (tt > a.rot_loss_t_threshold ? 1.0 : 0.0);
+  const double w_bb = a.bb_atom_loss_weight * (tt < a.bb_atom_loss_t_filter ? 1.0 : 0.0) * a.aux_loss_weight;
+  const double w_dm = a.dist_mat_loss_weight * (tt < a.dist_mat_loss_t_filter ? 1.0 : 0.0) * a.aux_loss_weight;
+  const double rsc = a.rot_scaling[b], tsc = a.trans_scaling[b];
+  for (int n = n0 + tid; n < n1; n += 256) {
+    const long long r = (long long)b * N + n;
+    const double dmk = 1.0 - (double)a.fixed_mask[r];
+    const double lm = (double)a.res_mask[r] * dmk;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const double e = a.gt_trans[r * 3 + k] - a.pred_trans[r * 3 + k] * dmk;
+      a.d_trans[r * 3 + k] = a.diffuse_trans ? -2.0 * e * lm / (tsc * tsc * denom) * (hi_t * a.trans_loss_weight * ws) * dmk : 0.0;
+      const double x0g = a.rigids_0[r * 7 + 4 + k] * a.coordinate_scaling, x0p = (double)a.pred_rigids[r * 7 + 4 + k] * a.coordinate_scaling;
+      a.d_rigids[r * 7 + 4 + k] =
+          (float)(a.diffuse_trans ? -2.0 * (x0g - x0p) * lm / denom * ((1.0 - hi_t) * a.trans_loss_weight * ws) * a.coordinate_scaling : 0.0);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) a.d_rigids[r * 7 + k] = 0.f;
+    double pr[3], gr[3], pa = 0.0, ga = 0.0;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { pr[k] = a.pred_rot[r * 3 + k] * dmk; gr[k] = a.gt_rot[r * 3 + k]; pa += pr[k] * pr[k]; ga += gr[k] * gr[k]; }
+    pa = sqrt(pa); ga = sqrt(ga);
+    double dpr[3];
+    if (a.separate_rot_loss) {
+      double dpax[3], dotp = 0.0;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) { dpax[k] = -2.0 * (gr[k] / (ga + 1e-6) - pr[k] / (pa + 1e-6)) * lm / denom * ws; dotp += dpax[k] * pr[k]; }
+      const double dpa = -2.0 * (ga - pa) * lm / (rsc * rsc * denom) * (wa * ws);
+      const double ipa_ = 1.0 / fmax(pa, 1e-30);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) dpr[k] = dpax[k] / (pa + 1e-6) - dotp / ((pa + 1e-6) * (pa + 1e-6)) * pr[k] * ipa_ + dpa * pr[k] * ipa_;
+    } else {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) dpr[k] = -2.0 * (gr[k] - pr[k]) * lm / (rsc * rsc * denom) * (wa * ws);
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) a.d_rot[r * 3 + k] = a.diffuse_rot ? dpr[k] * dmk : 0.0;
+    for (int k = 15; k < 111; ++k) a.d_atom37[r * 111 + k] = 0.f;
+  }
+  // rows p of this slab: backbone-atom term + pair term, one thread per row
+  const int M5 = 5 * N;
+  for (int p = 5 * n0 + tid; p < 5 * n1; p += 256) {
+    const int n = p / 5;
+    const long long r = (long long)b * N + n;
+    const float flp = S.fl[n], frp = S.fr[n];
+    const float gx = S.gt5[p * 3], gy = S.gt5[p * 3 + 1], gz = S.gt5[p * 3 + 2];
+    const float px = S.pr5[p * 3], py = S.pr5[p * 3 + 1], pz = S.pr5[p * 3 + 2];
+    const double bm = atom_present(S.gt5 + p * 3) ? (double)flp : 0.0;
+    const double cbb = 2.0 * bm / (bm_sum + 1e-10) * (w_bb * ws);
+    double ax = cbb * ((double)px - (double)gx), ay = cbb * ((double)py - (double)gy), az = cbb * ((double)pz - (double)gz);
+    if (w_dm != 0.0) {
+      for (int qx = 0; qx < M5; ++qx) {
+        const float flq = S.fl[qx / 5], frq = S.fr[qx / 5];
+        const float ex = gx - S.gt5[qx * 3], ey = gy - S.gt5[qx * 3 + 1], ez = gz - S.gt5[qx * 3 + 2];
+        const float gdist = sqrtf(ex * ex + ey * ey + ez * ez);
+        const float dxp = px - S.pr5[qx * 3], dyp = py - S.pr5[qx * 3 + 1], dzp = pz - S.pr5[qx * 3 + 2];
+        const float pdr = sqrtf(dxp * dxp + dyp * dyp + dzp * dzp);
+        if (!(pdr > 0.f)) continue;
+        double c = 0.0;
+        {   // ordered pair (p, q): mask fl_p fr_q [gd fl_p < 6], distances scaled by fl_p
+          const float gd = gdist * flp;
+          if (gd < 6.f && flp != 0.f && frq != 0.f)
+            c += -2.0 * ((double)gd - (double)pdr * (double)flp) * (double)(flp * frq) / pden * (w_dm * ws) * (double)flp / (double)pdr;
+        }
+        {   // ordered pair (q, p)
+          const float gd = gdist * flq;
+          if (gd < 6.f && flq != 0.f && frp != 0.f)
+            c += -2.0 * ((double)gd - (double)pdr * (double)flq) * (double)(flq * frp) / pden * (w_dm * ws) * (double)flq / (double)pdr;
+        }
+        ax += c * dxp; ay += c * dyp; az += c * dzp;
+      }
+    }
+    a.d_atom37[r * 111 + (p - 5 * n) * 3 + 0] = (float)ax;
+    a.d_atom37[r * 111 + (p - 5 * n) * 3 + 1] = (float)ay;
+    a.d_atom37[r * 111 + (p - 5 * n) * 3 + 2] = (float)az;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
 // Intermittent eval metrics on the device (analysis/metrics.py:120-132 ca_ca_distance / ca_ca_clashes): per backbone
 //   out[b] = { mean |d_i - 3.80209737096|, fraction of bonds d_i < 3.802 + tol_bond, number of CA pairs closer than tol_clash,
 //              fraction of such pairs among the pairs with distance > 0 }       d_i = |CA_i - CA_{i-1}|, valid residues first (mask prefix)

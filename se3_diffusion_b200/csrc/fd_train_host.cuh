@@ -146,9 +146,13 @@ struct TG {
     gemm(a, false);
   }
   // dW[Nout][lddw] += dy[rows,Nout]^T x[rows,Kin]   (atomic accumulation, split over the rows)
-  void wgrad(const float* dy, int lddy, const float* x, int ldx, float* dW, int lddw, int Nout, int Kin, long long rows, float alpha = 1.f) {
+  // mm3 path: the bias gradient can ride on the weight gradient (returns true if it did)
+  bool wgrad(const float* dy, int lddy, const float* x, int ldx, float* dW, int lddw, int Nout, int Kin, long long rows, float alpha = 1.f,
+             float* db = nullptr) {
     GemmArgs a;
     a.A = dy; a.lda = lddy; a.B = x; a.ldb = ldx; a.C = dW; a.ldc = lddw; a.M = Nout; a.N = Kin; a.K = (int)rows; a.atomic = 1; a.alpha = alpha;
+    const bool fused_bias = db != nullptr && h->train_gemm == 1 && 2.0 * Nout * Kin * (double)rows >= 3.0e7 && Nout >= 32 && Kin >= 16;
+    if (fused_bias) a.colsum_out = db;
     const bool big = Nout >= 96 && Kin >= 96;
     const int tile = big ? 128 : 64;
     const long long tiles = (long long)((Nout + tile - 1) / tile) * ((Kin + tile - 1) / tile);
@@ -158,6 +162,7 @@ struct TG {
     if (sp < 1) sp = 1;
     a.splits = (int)sp;
     gemm(a, false, false);
+    return fused_bias;
   }
   void bgrad(const float* dy, int lddy, long long rows, int Nout, float* db) {
     if (err) return;
@@ -168,8 +173,7 @@ struct TG {
   // full Linear backward: dW, db accumulate; dx (optional) = dy W
   void lin_bwd(const std::string& name, const float* x, int ldx, const float* dy, int lddy, int Nout, int Kin, long long M, float* dx = nullptr,
                int lddx = 0, bool accumulate = false, const float* relumask = nullptr, int ldm = 0) {
-    wgrad(dy, lddy, x, ldx, g(name + ".weight"), Kin, Nout, Kin, M);
-    bgrad(dy, lddy, M, Nout, g(name + ".bias"));
+    if (!wgrad(dy, lddy, x, ldx, g(name + ".weight"), Kin, Nout, Kin, M, 1.f, g(name + ".bias"))) bgrad(dy, lddy, M, Nout, g(name + ".bias"));
     if (dx) dgrad(dy, lddy, w(name + ".weight"), Kin, Nout, Kin, dx, lddx, M, accumulate, relumask, ldm);
   }
   void ln(int C, const float* x, int ldx, float* out, int ldo, const std::string& name, long long M, const float* rowmask = nullptr,
