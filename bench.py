@@ -45,7 +45,8 @@ def parse():
                    help="sample (default, the headline metric) | train: one optimiser step (fwd + DSM loss + bwd + all-reduce + Adam), BASELINE config 4")
     p.add_argument("--sweep", action="store_true", help="measure the other BASELINE configs (C1 paper weights, C2, C5 length sweep) in one run")
     p.add_argument("--lr", type=float, default=1e-4)
-    p.add_argument("--train-gemm", default="bf16x3", choices=["fp32", "bf16x3"], help="training-path GEMMs: CUDA-core fp32 or split-bf16 tensor cores")
+    p.add_argument("--train-gemm", default="tc", choices=["fp32", "bf16x3", "tc"],
+                   help="training-path GEMMs: CUDA-core fp32 | split-bf16 mma.sync | split-bf16 with the edge-tensor forward/dgrad GEMMs on tcgen05")
     return p.parse_args()
 
 
@@ -293,7 +294,7 @@ def run_train(args):
                 "e2e": {"value": world * B / e2e_s, "unit": "examples/s", "ms_per_step": e2e_s * 1e3, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8},
                 "comm_exposed_ms_per_step": exposed_ms, "allreduce_bytes_per_step": int(ts.grads.numel() * 4) if world > 1 else 0,
                 "final_loss": losses[-1] if losses else None, "clocks": clk,
-                "roofline": {"bound": "tensor", "kernel": "whole training step (forward + dgrad + wgrad GEMMs: %s)" % ("fp32 CUDA cores" if args.train_gemm == "fp32" else "mm3_kernel, mma.sync split-bf16"),
+                "roofline": {"bound": "tensor", "kernel": "whole training step (forward + dgrad + wgrad GEMMs: %s)" % {"fp32": "fp32 CUDA cores", "bf16x3": "mm3_kernel, mma.sync split-bf16", "tc": "edge-tensor forward/dgrad on tc_gemm_kernel (tcgen05), weight gradients and node path on mm3_kernel (mma.sync); split-bf16"}[args.train_gemm],
                              "achieved": ach, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": ach / pk["bf16_tflops_sustained"],
                              "peak_source": pk["source"], "traffic": None, "executed_flops_per_step": fl},
                 "cpu_baseline": cb}

@@ -288,7 +288,9 @@ int fd_train_release(fd_handle h);
 int64_t fd_workspace_bytes(fd_handle h, int which, int B, int N, int num_t, int aux);
 int64_t fd_debug_alloc_bytes(fd_handle h, int which);   /* developer aid: bytes of the arena `which` as currently allocated (0 = none) */
 /* Arithmetic of the training path's GEMMs: 0 = fp32 on the CUDA cores (default), 1 = split-bf16 (hi*hi + hi*lo + lo*hi, fp32 accumulate)
- * on the tensor cores — the accuracy class of FD_PREC_BF16X3; both meet the gradient tolerances of tests/test_gpu_train.py. */
+ * through mma.sync for every GEMM form, 2 = like 1 with the forward and data-gradient GEMMs over the edge tensor (EdgeTransition, edge
+ * embedder layers 2 and 4: 2/3 of the step's FLOPs) on tcgen05 (TMA-staged bf16 planes, TMEM accumulators) — the accuracy class of
+ * FD_PREC_BF16X3; all meet the gradient tolerances of tests/test_gpu_train.py. */
 int fd_train_set_gemm(fd_handle h, int mode);
 /* d total_loss / d model outputs for Experiment.loss_fn (train_se3_diffusion.py:538-680; total_loss = sum_b batch_loss[b] / #non-empty
  * samples): the gradient fd_train_backward starts from when the loss is not computed by torch. */

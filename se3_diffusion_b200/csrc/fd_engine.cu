@@ -1357,6 +1357,7 @@ static fd_train_state* train_state(fd_context* h) {
 static void free_train(fd_context* h) {
   if (!h->train) return;
   free_tape(h->train->tape);
+  ttc_free(h->train->tc);
   delete h->train;
   h->train = nullptr;
 }
@@ -1429,7 +1430,7 @@ extern "C" int64_t fd_debug_alloc_bytes(fd_handle h, int which) {
   return FD_EINVAL;
 }
 extern "C" int fd_train_set_gemm(fd_handle h, int mode) {
-  if (!h || (mode != 0 && mode != 1)) return fail(FD_EINVAL, "fd_train_set_gemm: mode %d", mode);
+  if (!h || mode < 0 || mode > 2) return fail(FD_EINVAL, "fd_train_set_gemm: mode %d", mode);
   h->train_gemm = mode;
   return FD_OK;
 }

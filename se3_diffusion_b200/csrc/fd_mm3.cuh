@@ -150,23 +150,31 @@ __global__ void __launch_bounds__(1024 / MT) mm3_kernel(const GemmArgs g) {
         bh[2 * np][0] = r[0]; bh[2 * np][1] = r[1]; bh[2 * np + 1][0] = r[2]; bh[2 * np + 1][1] = r[3];
         bl[2 * np][0] = s[0]; bl[2 * np][1] = s[1]; bl[2 * np + 1][0] = s[2]; bl[2 * np + 1][1] = s[3];
       }
+      uint32_t ah[MT][4], al[MT][4];
 #pragma unroll
       for (int mt = 0; mt < MT; ++mt) {
-        uint32_t ah[4], al[4];
         if (A_KMAJOR) {                          // smem [m][k]: matrices (m 0-7,k lo) (m 8-15,k lo) (m 0-7,k hi) (m 8-15,k hi)
           const uint32_t off = (uint32_t)((wm + mt * 16 + (mi & 1) * 8 + lr) * MM3_KSTRIDE + (ks * 2 + (mi >> 1)) * 16);
-          ldsm_x4(a_hi + off, ah); ldsm_x4(a_lo + off, al);
+          ldsm_x4(a_hi + off, ah[mt]); ldsm_x4(a_lo + off, al[mt]);
         } else {                                 // smem [k][m]: matrices (k lo,m 0-7) (k lo,m 8-15) (k hi,m 0-7) (k hi,m 8-15), transposed
           const uint32_t off = (uint32_t)((ks * 16 + (mi >> 1) * 8 + lr) * MM3_MSTRIDE + (wm + mt * 16 + (mi & 1) * 8) * 2);
-          ldsm_x4_t(a_hi + off, ah); ldsm_x4_t(a_lo + off, al);
-        }
-#pragma unroll
-        for (int nt = 0; nt < 4; ++nt) {
-          mma_bf16_16816(acc[mt][nt], ah[0], ah[1], ah[2], ah[3], bh[nt][0], bh[nt][1]);
-          mma_bf16_16816(acc[mt][nt], ah[0], ah[1], ah[2], ah[3], bl[nt][0], bl[nt][1]);
-          mma_bf16_16816(acc[mt][nt], al[0], al[1], al[2], al[3], bh[nt][0], bh[nt][1]);
+          ldsm_x4_t(a_hi + off, ah[mt]); ldsm_x4_t(a_lo + off, al[mt]);
         }
       }
+      // three passes, each over ALL of the warp's accumulator tiles: consecutive MMAs never target the same accumulator, so the
+      // dependent-issue latency of mma.sync (the top stall of the first version: "wait") is covered by the other tiles
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) mma_bf16_16816(acc[mt][nt], ah[mt][0], ah[mt][1], ah[mt][2], ah[mt][3], bh[nt][0], bh[nt][1]);
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) mma_bf16_16816(acc[mt][nt], ah[mt][0], ah[mt][1], ah[mt][2], ah[mt][3], bl[nt][0], bl[nt][1]);
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) mma_bf16_16816(acc[mt][nt], al[mt][0], al[mt][1], al[mt][2], al[mt][3], bh[nt][0], bh[nt][1]);
     }
     if (kt + 1 < nk) {
       store_tiles(buf ^ 1);

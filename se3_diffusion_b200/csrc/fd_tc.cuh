@@ -237,6 +237,9 @@ struct TcGemmParams {
   int b_row_s0, b_row_s1, b_k0, b_k_s1;
   long long o_s0, o_s1;               // output element offsets per (outer, inner)
   float alpha;                        // accumulator scale (0 = 1)
+  // training path (TC_EPI_F32 only): zero the output where relumask[m][n] <= 0 (backward of a ReLU whose OUTPUT is relumask); `rowadd`
+  // (edge-row node terms) is honoured by the fp32 epilogue as well
+  const float* relumask; int ldm;
 };
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -410,6 +413,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mA0h, const __grid_constant__
             const bool in = act && n + q * 4 < p.n_valid;     // n_valid is a multiple of 4 for every linear routed here
             bv[q] = (in && p.bias) ? __ldg(reinterpret_cast<const float4*>(p.bias + n + q * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
             rv[q] = (in && rrow) ? *reinterpret_cast<const float4*>(rrow + q * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            if (in && add_i) {
+              const float4 x = *reinterpret_cast<const float4*>(add_i + n + q * 4);
+              const float4 y = *reinterpret_cast<const float4*>(add_j + n + q * 4);
+              bv[q].x += x.x + y.x; bv[q].y += x.y + y.y; bv[q].z += x.z + y.z; bv[q].w += x.w + y.w;
+            }
           }
           uint32_t r[32];
           tmem_ld32(trow + (uint32_t)c0, r);
@@ -424,6 +432,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mA0h, const __grid_constant__
                 if (p.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
                 v.x *= rm; v.y *= rm; v.z *= rm; v.w *= rm;
                 v.x += rv[q].x; v.y += rv[q].y; v.z += rv[q].z; v.w += rv[q].w;
+                if (p.relumask) {
+                  const float4 mk = *reinterpret_cast<const float4*>(p.relumask + m * p.ldm + n + q * 4);
+                  v.x = mk.x > 0.f ? v.x : 0.f; v.y = mk.y > 0.f ? v.y : 0.f; v.z = mk.z > 0.f ? v.z : 0.f; v.w = mk.w > 0.f ? v.w : 0.f;
+                }
                 *reinterpret_cast<float4*>(orow + q * 4) = v;
               }
             }

@@ -70,6 +70,20 @@ __global__ void __launch_bounds__(128) edge_axis_sum_kernel(const float* __restr
   }
 }
 
+// fp32 weight block -> bf16 hi/lo planes for the tcgen05 GEMMs of the training path (rebuilt every step: the weights change).
+//   dst[r][dst_col0 + c] = split(transpose ? src[c*ld + r] : src[r*ld + c]),  r < rows, c < cols;  dst row stride dst_ld
+__global__ void pack_planes_kernel(const float* __restrict__ src, int ld, int rows, int cols, int transpose, __nv_bfloat16* __restrict__ hi,
+                                   __nv_bfloat16* __restrict__ lo, int dst_ld, int dst_col0) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * cols) return;
+  const int r = i / cols, c = i - r * cols;
+  const float v = transpose ? src[(long long)c * ld + r] : src[(long long)r * ld + c];
+  __nv_bfloat16 h, l;
+  split_bf16(v, h, l);
+  hi[(long long)r * dst_ld + dst_col0 + c] = h;
+  lo[(long long)r * dst_ld + dst_col0 + c] = l;
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 // LayerNorm backward (torch.nn.LayerNorm, eps 1e-5).  One warp per row, persistent grid; dgamma/dbeta accumulated in registers,
 // reduced per block in shared memory, one atomicAdd per channel per block.

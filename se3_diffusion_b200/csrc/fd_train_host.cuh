@@ -49,10 +49,28 @@ struct TrainTape {
 
 }  // namespace
 
+// tcgen05 path of the training step's big edge-row GEMMs (fd_train_set_gemm mode 2): forward and dgrad of the EdgeTransition / edge-embedder
+// linears run on tc_gemm_kernel (fd_tc.cuh: TMA-staged bf16 hi/lo planes, UMMA, TMEM accumulators, fp32 epilogue).  Activations are split
+// into plane scratch right before each GEMM; weight planes (and their transposes for the dgrads) are rebuilt from the fp32 arena each step.
+struct TrainTcMat { __nv_bfloat16 *hi = nullptr, *lo = nullptr; CUtensorMap mh, ml; int rows = 0, cols = 0; };
+struct TrainTcLayer { TrainTcMat w1z, w2, wfx, wft, w2t, dzw; };
+struct TrainTc {
+  bool weights_ready = false;
+  char* warena = nullptr;
+  TrainTcLayer et[NBLK - 1];
+  TrainTcMat ee2, ee4, ee2t, ee4t;
+  // activation plane scratch (sized for the tape's E)
+  long long E = 0;
+  char* sarena = nullptr;
+  __nv_bfloat16 *s0h = nullptr, *s0l = nullptr, *s1h = nullptr, *s1l = nullptr;    // [E,384], [E,128]
+  CUtensorMap m0h, m0l, m1h, m1l;
+};
+
 struct fd_train_state {
   float* P = nullptr;      // bound parameter arena (device, caller-owned)
   float* G = nullptr;      // bound gradient arena
   TrainTape tape;
+  TrainTc tc;
 };
 
 static fd_train_state* train_state(fd_context* h);
@@ -125,7 +143,7 @@ struct TG {
   }
   void gemm(GemmArgs a, bool b_kmajor, bool a_kmajor = true) {
     if (err) return;
-    cudaError_t e = h->train_gemm == 1 ? launch_gemm_mm3(a, b_kmajor, st, a_kmajor) : launch_gemm(a, b_kmajor, st, a_kmajor);
+    cudaError_t e = h->train_gemm >= 1 ? launch_gemm_mm3(a, b_kmajor, st, a_kmajor) : launch_gemm(a, b_kmajor, st, a_kmajor);
     h->launches++;
     if (e != cudaSuccess) err = fail(FD_ECUDA, "gemm launch failed: %s", cudaGetErrorString(e));
   }
@@ -151,7 +169,7 @@ struct TG {
              float* db = nullptr) {
     GemmArgs a;
     a.A = dy; a.lda = lddy; a.B = x; a.ldb = ldx; a.C = dW; a.ldc = lddw; a.M = Nout; a.N = Kin; a.K = (int)rows; a.atomic = 1; a.alpha = alpha;
-    const bool fused_bias = db != nullptr && h->train_gemm == 1 && 2.0 * Nout * Kin * (double)rows >= 3.0e7 && Nout >= 32 && Kin >= 16;
+    const bool fused_bias = db != nullptr && h->train_gemm >= 1 && 2.0 * Nout * Kin * (double)rows >= 3.0e7 && Nout >= 32 && Kin >= 16;
     if (fused_bias) a.colsum_out = db;
     const bool big = Nout >= 96 && Kin >= 96;
     const int tile = big ? 128 : 64;
@@ -196,6 +214,32 @@ struct TG {
     h->launches++;
     if (e != cudaSuccess) err = fail(FD_ECUDA, "layernorm backward launch failed: %s", cudaGetErrorString(e));
   }
+  // ---- tcgen05 path (mode 2) ----
+  bool tc_on() const { return h->train_gemm == 2; }
+  void pack(TrainTcMat& m, const float* src, int ld, int rows, int cols, bool transpose, int col0 = 0) {
+    if (err) return;
+    pack_planes_kernel<<<(rows * cols + 255) / 256, 256, 0, st>>>(src, ld, rows, cols, transpose ? 1 : 0, m.hi, m.lo, m.cols, col0);
+    ck("pack_planes");
+  }
+  void split(const float* x, int ld, long long M, int K, __nv_bfloat16* hi, __nv_bfloat16* lo) {
+    if (err) return;
+    const long long n4 = M * (K / 4);
+    split_planes_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(x, ld, M, K, hi, lo);
+    ck("split_planes");
+  }
+  // out[M, W.rows] = epi( [A0 | A1] W^T ) through tc_gemm_kernel; A0 = KB0 k-blocks of map (a0h,a0l), A1 = KB1 k-blocks of (a1h,a1l)
+  void tc_gemm(const CUtensorMap& a0h, const CUtensorMap& a0l, int KB0, const CUtensorMap& a1h, const CUtensorMap& a1l, int KB1, const TrainTcMat& W,
+               long long M, float* out, int ldo, const float* bias, bool relu, const float* rowadd, int off_i, int off_j, int nres,
+               const float* relumask, int ldm) {
+    if (err) return;
+    TcGemmParams p{};
+    p.M = (int)M; p.N = W.rows; p.KB0 = KB0; p.KB1 = KB1; p.planes = 2; p.epi = TC_EPI_F32; p.bias = bias; p.relu = relu ? 1 : 0;
+    p.rowadd = rowadd; p.off_i = off_i; p.off_j = off_j; p.ld_rowadd = ET_NODE; p.nres = nres;
+    p.m_tiles = (int)((M + TC_BM - 1) / TC_BM);
+    const int chunks = W.rows / TC_NC;
+    p.nch = 1; p.num_tiles = p.m_tiles * chunks; p.n_valid = W.rows; p.out_f32 = out; p.ldo = ldo; p.relumask = relumask; p.ldm = ldm;
+    if (tc_launch_maps(a0h, a0l, a1h, a1l, W.mh, W.ml, p, st, &h->launches)) err = fail(FD_ECUDA, "training tcgen05 GEMM launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+  }
   void copy(float* dst, int ldd, const float* src, int lds, int C, long long M, const float* rowmask = nullptr, bool accumulate = false) {
     if (err) return;
     copy_cols_kernel<<<(unsigned)((M * C + 255) / 256), 256, 0, st>>>(dst, ldd, src, lds, C, M, rowmask, accumulate ? 1 : 0);
@@ -209,6 +253,50 @@ struct TG {
 };
 
 static const std::string kTrunk = "score_model.trunk.";
+
+// ---- tcgen05 helpers of the training path ---------------------------------------------------------------------------------------
+static int ttc_alloc_weights(TrainTc& T) {
+  if (T.warena) return FD_OK;
+  auto bytes = [](int rows, int cols) { return al256((size_t)rows * cols * 2); };
+  size_t total = 0;
+  const int dims[6][2] = {{ET_HID, C_Z}, {ET_HID, ET_HID}, {C_Z, ET_HID + C_Z}, {ET_HID, C_Z}, {ET_HID, ET_HID}, {C_Z, ET_HID + C_Z}};
+  for (int l = 0; l < NBLK - 1; ++l) for (auto& d : dims) total += 2 * bytes(d[0], d[1]);
+  total += 4 * 2 * bytes(C_Z, C_Z);
+  if (cudaMalloc(&T.warena, total) != cudaSuccess) { cudaGetLastError(); return fail(FD_ENOMEM, "training weight planes allocation failed"); }
+  char* p = T.warena;
+  auto carve = [&](TrainTcMat& m, int rows, int cols) -> int {
+    m.rows = rows; m.cols = cols;
+    m.hi = reinterpret_cast<__nv_bfloat16*>(p); p += bytes(rows, cols);
+    m.lo = reinterpret_cast<__nv_bfloat16*>(p); p += bytes(rows, cols);
+    return tc_make_map(&m.mh, m.hi, rows, cols) | tc_make_map(&m.ml, m.lo, rows, cols);
+  };
+  int rc = 0;
+  for (int l = 0; l < NBLK - 1; ++l) {
+    TrainTcLayer& L = T.et[l];
+    rc |= carve(L.w1z, ET_HID, C_Z); rc |= carve(L.w2, ET_HID, ET_HID); rc |= carve(L.wfx, C_Z, ET_HID + C_Z);
+    rc |= carve(L.wft, ET_HID, C_Z); rc |= carve(L.w2t, ET_HID, ET_HID); rc |= carve(L.dzw, C_Z, ET_HID + C_Z);
+  }
+  rc |= carve(T.ee2, C_Z, C_Z); rc |= carve(T.ee4, C_Z, C_Z); rc |= carve(T.ee2t, C_Z, C_Z); rc |= carve(T.ee4t, C_Z, C_Z);
+  return rc ? fail(FD_ECUDA, "cuTensorMapEncodeTiled failed for the training weight planes") : FD_OK;
+}
+static int ttc_ensure_scratch(TrainTc& T, long long E) {
+  if (T.sarena && T.E == E) return FD_OK;
+  if (T.sarena) { cudaDeviceSynchronize(); cudaFree(T.sarena); T.sarena = nullptr; }
+  const size_t b0 = al256((size_t)E * ET_HID * 2), b1 = al256((size_t)E * C_Z * 2);
+  if (cudaMalloc(&T.sarena, 2 * b0 + 2 * b1) != cudaSuccess) { cudaGetLastError(); return fail(FD_ENOMEM, "training plane scratch allocation failed"); }
+  T.E = E;
+  char* p = T.sarena;
+  T.s0h = reinterpret_cast<__nv_bfloat16*>(p); p += b0; T.s0l = reinterpret_cast<__nv_bfloat16*>(p); p += b0;
+  T.s1h = reinterpret_cast<__nv_bfloat16*>(p); p += b1; T.s1l = reinterpret_cast<__nv_bfloat16*>(p);
+  const int rc = tc_make_map(&T.m0h, T.s0h, E, ET_HID) | tc_make_map(&T.m0l, T.s0l, E, ET_HID) | tc_make_map(&T.m1h, T.s1h, E, C_Z) |
+                 tc_make_map(&T.m1l, T.s1l, E, C_Z);
+  return rc ? fail(FD_ECUDA, "cuTensorMapEncodeTiled failed for the training plane scratch") : FD_OK;
+}
+static void ttc_free(TrainTc& T) {
+  if (T.warena) cudaFree(T.warena);
+  if (T.sarena) cudaFree(T.sarena);
+  T = TrainTc();
+}
 
 }  // namespace
 
@@ -225,6 +313,27 @@ static int train_forward_impl(fd_context* h, fd_train_state* S, int B, int N, co
   const float* res_mask = in->res_mask;
   T.rigids_t = in->rigids_t; T.res_mask = in->res_mask; T.fixed_mask = in->fixed_mask; T.gt_psi = in->gt_psi; T.t = in->t; T.t_is_f32 = in->t_is_f32;
   const std::string e = "embedding_layer.";
+  TrainTc& C = S->tc;
+  if (f.tc_on()) {
+    CKI(ttc_alloc_weights(C));
+    CKI(ttc_ensure_scratch(C, E));
+    // weight planes of this step (the optimiser changed the fp32 arena): forward forms and the transposed forms the dgrads read
+    f.pack(C.ee2, f.w(e + "edge_embedder.2.weight"), C_Z, C_Z, C_Z, false); f.pack(C.ee2t, f.w(e + "edge_embedder.2.weight"), C_Z, C_Z, C_Z, true);
+    f.pack(C.ee4, f.w(e + "edge_embedder.4.weight"), C_Z, C_Z, C_Z, false); f.pack(C.ee4t, f.w(e + "edge_embedder.4.weight"), C_Z, C_Z, C_Z, true);
+    for (int l = 0; l < NBLK - 1; ++l) {
+      const std::string p = kTrunk + "edge_transition_" + std::to_string(l) + ".";
+      const float *W1 = f.w(p + "trunk.0.weight"), *W2 = f.w(p + "trunk.2.weight"), *Wf = f.w(p + "final_layer.weight");
+      TrainTcLayer& L = C.et[l];
+      f.pack(L.w1z, W1, ET_HID, ET_HID, C_Z, false);                  // W1[:, :128]                       [384][128]
+      f.pack(L.w2, W2, ET_HID, ET_HID, ET_HID, false);                //                                    [384][384]
+      f.pack(L.wfx, Wf, ET_HID, C_Z, ET_HID, false, 0);               // [Wf | Wf[:, :128]]                 [128][512]
+      f.pack(L.wfx, Wf, ET_HID, C_Z, C_Z, false, ET_HID);
+      f.pack(L.wft, Wf, ET_HID, ET_HID, C_Z, true);                   // Wf^T                               [384][128]
+      f.pack(L.w2t, W2, ET_HID, ET_HID, ET_HID, true);                // W2^T                               [384][384]
+      f.pack(L.dzw, W1, ET_HID, C_Z, ET_HID, true, 0);                // [W1[:, :128]^T | Wf[:, :128]^T]    [128][512]
+      f.pack(L.dzw, Wf, ET_HID, C_Z, C_Z, true, ET_HID);
+    }
+  }
   // ---- embedders (model/score_network.py:103-154) ----
   node_feats_kernel<<<(unsigned)((R * 16 + 255) / 256), 256, 0, st>>>(in->t, in->t_is_f32, in->fixed_mask, in->seq_idx, T.node_in, T.temb, B, N);
   f.ck("node_feats");
@@ -235,8 +344,15 @@ static int train_forward_impl(fd_context* h, fd_train_state* S, int B, int N, co
   pair_feats_kernel<<<dim3((unsigned)R, (N + 7) / 8), 256, 0, st>>>(T.temb, in->fixed_mask, in->seq_idx, in->sc_ca_t, T.pair, N);
   f.ck("pair_feats");
   f.lin(T.pair, EDGE_IN, f.w(e + "edge_embedder.0.weight"), EDGE_IN, f.w(e + "edge_embedder.0.bias"), EDGE_IN, C_Z, T.ee_h1, C_Z, E, true);
-  f.lin(T.ee_h1, C_Z, f.w(e + "edge_embedder.2.weight"), C_Z, f.w(e + "edge_embedder.2.bias"), C_Z, C_Z, T.ee_h2, C_Z, E, true);
-  f.lin(T.ee_h2, C_Z, f.w(e + "edge_embedder.4.weight"), C_Z, f.w(e + "edge_embedder.4.bias"), C_Z, C_Z, T.ee_y, C_Z, E);
+  if (f.tc_on()) {
+    f.split(T.ee_h1, C_Z, E, C_Z, C.s1h, C.s1l);
+    f.tc_gemm(C.m1h, C.m1l, 2, C.m1h, C.m1l, 0, C.ee2, E, T.ee_h2, C_Z, f.w(e + "edge_embedder.2.bias"), true, nullptr, 0, 0, N, nullptr, 0);
+    f.split(T.ee_h2, C_Z, E, C_Z, C.s1h, C.s1l);
+    f.tc_gemm(C.m1h, C.m1l, 2, C.m1h, C.m1l, 0, C.ee4, E, T.ee_y, C_Z, f.w(e + "edge_embedder.4.bias"), false, nullptr, 0, 0, N, nullptr, 0);
+  } else {
+    f.lin(T.ee_h1, C_Z, f.w(e + "edge_embedder.2.weight"), C_Z, f.w(e + "edge_embedder.2.bias"), C_Z, C_Z, T.ee_h2, C_Z, E, true);
+    f.lin(T.ee_h2, C_Z, f.w(e + "edge_embedder.4.weight"), C_Z, f.w(e + "edge_embedder.4.bias"), C_Z, C_Z, T.ee_y, C_Z, E);
+  }
   f.ln(128, T.ee_y, C_Z, T.z[0], C_Z, e + "edge_embedder.5", E, nullptr, res_mask, N);
   init_frames_kernel<<<(unsigned)((R + 255) / 256), 256, 0, st>>>(in->rigids_t, T.blk[0].quat_in, T.blk[0].trans_in, R);
   f.ck("init_frames");
@@ -340,6 +456,15 @@ static int train_forward_impl(fd_context* h, fd_train_state* S, int B, int N, co
       f.lin(X.nb, C_Z, W1 + 2 * C_Z, ET_HID, nullptr, C_Z, ET_HID, X.pquv + ET_HID, ET_NODE, R);                          // Q_j
       f.lin(X.nb, C_Z, Wf + C_Z, ET_HID, f.w(p + "final_layer.bias"), C_Z, C_Z, X.pquv + 2 * ET_HID, ET_NODE, R);          // U_i (+ bf)
       f.lin(X.nb, C_Z, Wf + 2 * C_Z, ET_HID, nullptr, C_Z, C_Z, X.pquv + 2 * ET_HID + C_Z, ET_NODE, R);                   // V_j
+      if (f.tc_on()) {
+        TrainTcLayer& L = C.et[b];
+        f.split(T.z[b], C_Z, E, C_Z, C.s1h, C.s1l);
+        f.tc_gemm(C.m1h, C.m1l, 2, C.m1h, C.m1l, 0, L.w1z, E, X.h1, ET_HID, nullptr, true, X.pquv, 0, ET_HID, N, nullptr, 0);               // h1
+        f.split(X.h1, ET_HID, E, ET_HID, C.s0h, C.s0l);
+        f.tc_gemm(C.m0h, C.m0l, 6, C.m0h, C.m0l, 0, L.w2, E, X.h2, ET_HID, f.w(p + "trunk.2.bias"), true, nullptr, 0, 0, N, nullptr, 0);     // h2
+        f.split(X.h2, ET_HID, E, ET_HID, C.s0h, C.s0l);
+        f.tc_gemm(C.m0h, C.m0l, 6, C.m1h, C.m1l, 2, L.wfx, E, X.ety, C_Z, nullptr, false, X.pquv, 2 * ET_HID, 2 * ET_HID + C_Z, N, nullptr, 0);   // y
+      } else {
       GemmArgs g;   // h1 = relu(z W1z^T + P_i + Q_j)
       g.A = T.z[b]; g.lda = C_Z; g.B = W1; g.ldb = ET_HID; g.C = X.h1; g.ldc = ET_HID; g.M = (int)E; g.N = ET_HID; g.K = C_Z; g.relu = 1;
       g.rowadd_i = X.pquv; g.rowadd_j = X.pquv + ET_HID; g.ld_rowadd = ET_NODE; g.nres = N; g.row_offset = 0;
@@ -350,6 +475,7 @@ static int train_forward_impl(fd_context* h, fd_train_state* S, int B, int N, co
       y.rowadd_i = X.pquv + 2 * ET_HID; y.rowadd_j = X.pquv + 2 * ET_HID + C_Z; y.ld_rowadd = ET_NODE; y.nres = N; y.row_offset = 0;
       f.gemm(y, true);
       f.lin(X.h2, ET_HID, Wf, ET_HID, nullptr, ET_HID, C_Z, X.ety, C_Z, E, false, nullptr, 0, nullptr, true);            // y += h2 Wf^T
+      }
       f.ln(128, X.ety, C_Z, T.z[b + 1], C_Z, p + "layer_norm", E, nullptr, res_mask, N);
     }
   }
@@ -516,12 +642,25 @@ static void edge_transition_backward(fd_context* h, TG& f, TrainTape& T, int b, 
   const std::string p = kTrunk + "edge_transition_" + std::to_string(b) + ".";
   const float *W1 = f.w(p + "trunk.0.weight"), *Wf = f.w(p + "final_layer.weight");
   float *dW1 = f.g(p + "trunk.0.weight"), *dWf = f.g(p + "final_layer.weight");
+  TrainTc& C = train_state(h)->tc;
   f.ln_bwd(128, X.ety, C_Z, dz_in, C_Z, T.dy128, C_Z, p + "layer_norm", E, nullptr, T.res_mask, N);                  // dy
-  f.dgrad(T.dy128, C_Z, Wf, ET_HID, C_Z, ET_HID, T.dh384a, ET_HID, E, false, X.h2, ET_HID);                          // dh2 = (dy Wf) * (h2 > 0)
-  f.wgrad(T.dy128, C_Z, X.h2, ET_HID, dWf, ET_HID, C_Z, ET_HID, E);
+  if (f.tc_on()) {
+    TrainTcLayer& L = C.et[b];
+    f.split(T.dy128, C_Z, E, C_Z, C.s1h, C.s1l);
+    f.tc_gemm(C.m1h, C.m1l, 2, C.m1h, C.m1l, 0, L.wft, E, T.dh384a, ET_HID, nullptr, false, nullptr, 0, 0, N, X.h2, ET_HID);        // dh2 = (dy Wf) * (h2 > 0)
+  } else {
+    f.dgrad(T.dy128, C_Z, Wf, ET_HID, C_Z, ET_HID, T.dh384a, ET_HID, E, false, X.h2, ET_HID);
+  }
+  if (!f.wgrad(T.dy128, C_Z, X.h2, ET_HID, dWf, ET_HID, C_Z, ET_HID, E, 1.f, f.g(p + "final_layer.bias"))) f.bgrad(T.dy128, C_Z, E, C_Z, f.g(p + "final_layer.bias"));
   f.wgrad(T.dy128, C_Z, T.z[b], C_Z, dWf, ET_HID, C_Z, C_Z, E);
-  f.bgrad(T.dy128, C_Z, E, C_Z, f.g(p + "final_layer.bias"));
-  f.lin_bwd(p + "trunk.2", X.h1, ET_HID, T.dh384a, ET_HID, ET_HID, ET_HID, E, T.dh384b, ET_HID, false, X.h1, ET_HID);   // dh1
+  if (f.tc_on()) {
+    TrainTcLayer& L = C.et[b];
+    f.wgrad(T.dh384a, ET_HID, X.h1, ET_HID, f.g(p + "trunk.2.weight"), ET_HID, ET_HID, ET_HID, E, 1.f, f.g(p + "trunk.2.bias"));
+    f.split(T.dh384a, ET_HID, E, ET_HID, C.s0h, C.s0l);
+    f.tc_gemm(C.m0h, C.m0l, 6, C.m0h, C.m0l, 0, L.w2t, E, T.dh384b, ET_HID, nullptr, false, nullptr, 0, 0, N, X.h1, ET_HID);        // dh1 = (dh2 W2) * (h1 > 0)
+  } else {
+    f.lin_bwd(p + "trunk.2", X.h1, ET_HID, T.dh384a, ET_HID, ET_HID, ET_HID, E, T.dh384b, ET_HID, false, X.h1, ET_HID);   // dh1
+  }
   if (f.err) return;
   edge_axis_sum_kernel<<<(unsigned)R, 128, 0, st>>>(T.dy128, T.RSy, N, C_Z, 0); f.ck("edge_axis_sum");
   edge_axis_sum_kernel<<<(unsigned)R, 128, 0, st>>>(T.dy128, T.CSy, N, C_Z, 1); f.ck("edge_axis_sum");
@@ -533,8 +672,13 @@ static void edge_transition_backward(fd_context* h, TG& f, TrainTape& T, int b, 
   f.bgrad(T.RS1, ET_HID, R, ET_HID, f.g(p + "trunk.0.bias"));
   f.wgrad(T.RSy, C_Z, X.nb, C_Z, dWf + C_Z, ET_HID, C_Z, C_Z, R);
   f.wgrad(T.CSy, C_Z, X.nb, C_Z, dWf + 2 * C_Z, ET_HID, C_Z, C_Z, R);
-  f.dgrad(T.dh384b, ET_HID, W1, ET_HID, ET_HID, C_Z, dz_out, C_Z, E);                    // dz = dh1 W1[:, :128]
-  f.dgrad(T.dy128, C_Z, Wf, ET_HID, C_Z, C_Z, dz_out, C_Z, E, true);                     //    + dy Wf[:, :128]
+  if (f.tc_on()) {
+    f.split(T.dh384b, ET_HID, E, ET_HID, C.s0h, C.s0l);                                    // s1 still holds dy's planes
+    f.tc_gemm(C.m0h, C.m0l, 6, C.m1h, C.m1l, 2, C.et[b].dzw, E, dz_out, C_Z, nullptr, false, nullptr, 0, 0, N, nullptr, 0);    // dz = dh1 W1[:, :128] + dy Wf[:, :128]
+  } else {
+    f.dgrad(T.dh384b, ET_HID, W1, ET_HID, ET_HID, C_Z, dz_out, C_Z, E);                    // dz = dh1 W1[:, :128]
+    f.dgrad(T.dy128, C_Z, Wf, ET_HID, C_Z, C_Z, dz_out, C_Z, E, true);                     //    + dy Wf[:, :128]
+  }
   f.dgrad(T.RS1, ET_HID, W1 + C_Z, ET_HID, ET_HID, C_Z, T.dnb, C_Z, R);
   f.dgrad(T.CS1, ET_HID, W1 + 2 * C_Z, ET_HID, ET_HID, C_Z, T.dnb, C_Z, R, true);
   f.dgrad(T.RSy, C_Z, Wf + C_Z, ET_HID, C_Z, C_Z, T.dnb, C_Z, R, true);
@@ -621,8 +765,18 @@ static int train_backward_impl(fd_context* h, fd_train_state* S, const fd_train_
       f.wgrad(T.tC, 256, T.node_in, NODE_IN_PAD, f.g(e + "node_embedder.0.weight"), NODE_IN, 256, NODE_IN, R);
       f.bgrad(T.tC, 256, R, 256, f.g(e + "node_embedder.0.bias"));
       f.ln_bwd(128, T.ee_y, C_Z, dz_cur, C_Z, T.dy128, C_Z, e + "edge_embedder.5", E, nullptr, res_mask, N);
-      f.lin_bwd(e + "edge_embedder.4", T.ee_h2, C_Z, T.dy128, C_Z, C_Z, C_Z, E, T.dee, C_Z, false, T.ee_h2, C_Z);
-      f.lin_bwd(e + "edge_embedder.2", T.ee_h1, C_Z, T.dee, C_Z, C_Z, C_Z, E, T.dy128, C_Z, false, T.ee_h1, C_Z);
+      if (f.tc_on()) {
+        TrainTc& C = S->tc;
+        f.lin_bwd(e + "edge_embedder.4", T.ee_h2, C_Z, T.dy128, C_Z, C_Z, C_Z, E);                  // weight / bias gradients only
+        f.split(T.dy128, C_Z, E, C_Z, C.s1h, C.s1l);
+        f.tc_gemm(C.m1h, C.m1l, 2, C.m1h, C.m1l, 0, C.ee4t, E, T.dee, C_Z, nullptr, false, nullptr, 0, 0, N, T.ee_h2, C_Z);
+        f.lin_bwd(e + "edge_embedder.2", T.ee_h1, C_Z, T.dee, C_Z, C_Z, C_Z, E);
+        f.split(T.dee, C_Z, E, C_Z, C.s1h, C.s1l);
+        f.tc_gemm(C.m1h, C.m1l, 2, C.m1h, C.m1l, 0, C.ee2t, E, T.dy128, C_Z, nullptr, false, nullptr, 0, 0, N, T.ee_h1, C_Z);
+      } else {
+        f.lin_bwd(e + "edge_embedder.4", T.ee_h2, C_Z, T.dy128, C_Z, C_Z, C_Z, E, T.dee, C_Z, false, T.ee_h2, C_Z);
+        f.lin_bwd(e + "edge_embedder.2", T.ee_h1, C_Z, T.dee, C_Z, C_Z, C_Z, E, T.dy128, C_Z, false, T.ee_h1, C_Z);
+      }
       f.wgrad(T.dy128, C_Z, T.pair, EDGE_IN, f.g(e + "edge_embedder.0.weight"), EDGE_IN, C_Z, EDGE_IN, E);
       f.bgrad(T.dy128, C_Z, E, C_Z, f.g(e + "edge_embedder.0.bias"));
     }

@@ -552,8 +552,8 @@ def _adam_step(self, params: torch.Tensor, grads: torch.Tensor, exp_avg: torch.T
 
 
 def _train_set_gemm(self, mode: str):
-    """'fp32' (CUDA cores) or 'bf16x3' (split-bf16 tensor cores) for the training path's GEMMs."""
-    check(self.lib.fd_train_set_gemm(self._h, {"fp32": 0, "bf16x3": 1}[mode]))
+    """'fp32' (CUDA cores), 'bf16x3' (split-bf16 mma.sync for every GEMM) or 'tc' (bf16x3 with the edge-tensor forward / dgrad GEMMs on tcgen05)."""
+    check(self.lib.fd_train_set_gemm(self._h, {"fp32": 0, "bf16x3": 1, "tc": 2}[mode]))
     self.train_gemm = mode
 
 

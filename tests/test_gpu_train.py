@@ -39,10 +39,11 @@ def _oracle_autograd(batch):
     return w, wa, out, total
 
 
-@pytest.mark.parametrize("gemm", ["fp32", "bf16x3"])
+@pytest.mark.parametrize("gemm", ["fp32", "bf16x3", "tc"])
 @pytest.mark.parametrize("tag", ["a", "b"])
 def test_train_forward_and_backward_vs_oracle_autograd(tag, gemm):
-    """gemm = fp32: CUDA-core GEMMs; bf16x3: the split-bf16 mma.sync tensor-core GEMM (fd_mm3.cuh) in all three operand forms."""
+    """gemm = fp32: CUDA-core GEMMs; bf16x3: the split-bf16 mma.sync tensor-core GEMM (fd_mm3.cuh) in all three operand forms; tc: the edge-tensor
+    forward / data-gradient GEMMs on tcgen05 (tc_gemm_kernel over bf16 planes), the rest as bf16x3."""
     from se3_diffusion_b200.engine import views_of
     e, g, batch, flat, grads = _setup(tag, gemm)
     w, wa, ref, total = _oracle_autograd(batch)
