@@ -731,3 +731,15 @@ def test_forward_use_cached_score_lookup(eng):
     assert (rel < 1e-4).mean() > 0.97, f"only {(rel < 1e-4).mean():.3f} of the residues agree"
     assert rel.max() < 0.2                      # a neighbouring bucket, not garbage
     assert_close(out["trans_score"].cpu().numpy(), ref["trans_score"].numpy(), 0, norm_rel=1e-4, name="trans_score")
+
+
+def test_sample_sharded_single_process_equals_sample_device(eng):
+    """parallel.sample_sharded on the real engine (world size 1: no process group): same samples as the direct device loop, and a
+    sub-range of the batch reproduces the corresponding samples of the full batch (the property the multi-GPU split relies on)."""
+    from se3_diffusion_b200.parallel import sample_sharded, shard_range
+    a37, rig, ms, nl = sample_sharded(eng, 4, 40, num_t=5, seed=21)
+    b37, brig, _, _ = eng.sample_device(4, 40, num_t=5, seed=21, first_sample=0)
+    assert torch.equal(a37, b37) and torch.equal(rig, brig)
+    first, count = shard_range(4, 2, 1)
+    c37, _, _, _ = eng.sample_device(count, 40, num_t=5, seed=21, first_sample=first)
+    assert_close(c37.cpu().numpy(), a37[first:first + count].cpu().numpy(), 0, norm_rel=1e-5, name="rank-1 shard of a 2-way split")

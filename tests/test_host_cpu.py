@@ -229,3 +229,20 @@ dist.destroy_process_group()
     outs = [p.communicate(timeout=300) for p in procs]
     for r, (o, e) in enumerate(outs):
         assert f"DDP-LOGIC-OK {r}" in o, o + e
+
+
+def test_linear_initialisers_follow_the_reference_distribution():
+    """`_Linear` inits (model/ipa_pytorch.py:101-166): 'default' = LeCun truncated normal (std^2 = 1/fan_in after the
+    truncation correction), 'relu' = He (2/fan_in), 'final' = zeros, biases zero."""
+    from se3_diffusion_b200.score_network import _Linear
+    torch.manual_seed(0)
+    for init, scale in (("default", 1.0), ("relu", 2.0)):
+        lin = _Linear(512, 768, init)
+        w = lin.weight.detach().numpy()
+        assert abs(w.std() - np.sqrt(scale / 512)) < 0.02 * np.sqrt(scale / 512), (init, w.std())
+        assert np.abs(w).max() <= 2.0 * np.sqrt(scale / 512) / 0.87962566103423978 + 1e-6      # truncated at +-2 sigma of the parent normal
+        assert float(lin.bias.abs().max()) == 0.0
+    lin = _Linear(64, 32, "final")
+    assert float(lin.weight.abs().max()) == 0.0
+    with pytest.raises(ValueError):
+        _Linear(4, 4, "nonsense")
