@@ -194,6 +194,17 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
   return d;
 }
 // kind::f16 instruction descriptor: D = f32, A = B = bf16, both K-major, M = 128, N = 128
+// MN-major SWIZZLE_128B operand (cute: Swizzle<3,4,3> o ((8,n),(8,k)) : ((1,LBO),(8,SBO)) in 16-byte units): a K row holds 64 contiguous MN
+// elements (128 B); the next 64 MN elements live LBO bytes further (here: the second TMA box, 8 KB), the next group of 8 K rows SBO = 1 KB further
+__device__ __forceinline__ uint64_t make_sw128_desc_mn(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFFu);
+  d |= (uint64_t)(8192 >> 4) << 16;                     // LBO
+  d |= (uint64_t)(1024 >> 4) << 32;                     // SBO
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
 __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
@@ -240,6 +251,9 @@ struct TcGemmParams {
   // training path (TC_EPI_F32 only): zero the output where relumask[m][n] <= 0 (backward of a ReLU whose OUTPUT is relumask); `rowadd`
   // (edge-row node terms) is honoured by the fp32 epilogue as well
   const float* relumask; int ldm;
+  int mn_major;                       // both operands are MN-major: planes [K rows, MN columns] (an activation tensor [rows, C] contracted over its
+                                      // ROWS — the weight gradient dW = dy^T x — read in place, no transposed copy): TMA boxes {64 MN, 64 K}, two per
+                                      // 128-wide tile, UMMA descriptors with LBO = 8 KB (next 64-column block) and SBO = 1 KB (next 8 K rows)
   int atomic;                         // out_f32[m][n] += alpha*acc through atomicAdd (weight gradients: the k-slices of one output tile are
                                       // the batched mode's inner batches with o_s1 = 0); bias / relu / mask / residual are ignored
 };
@@ -310,8 +324,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mA0h, const __grid_constant__
           const uint32_t dstA = a_ring + sa * 2 * TC_PLANE_BYTES;
           if (elect_one()) {
             mbar_expect_tx(a_full(sa), stage_bytes);
-            tma_load_2d(dstA, first ? &mA0h : &mA1h, a_full(sa), ka, m0);
-            if (p.planes == 2) tma_load_2d(dstA + TC_PLANE_BYTES, first ? &mA0l : &mA1l, a_full(sa), ka, m0);
+            if (p.mn_major) {       // inner coordinate = MN (channel), row coordinate = K (row of the activation tensor)
+              tma_load_2d(dstA, &mA0h, a_full(sa), m0, ka); tma_load_2d(dstA + 8192u, &mA0h, a_full(sa), m0 + 64, ka);
+              tma_load_2d(dstA + TC_PLANE_BYTES, &mA0l, a_full(sa), m0, ka); tma_load_2d(dstA + TC_PLANE_BYTES + 8192u, &mA0l, a_full(sa), m0 + 64, ka);
+            } else {
+              tma_load_2d(dstA, first ? &mA0h : &mA1h, a_full(sa), ka, m0);
+              if (p.planes == 2) tma_load_2d(dstA + TC_PLANE_BYTES, first ? &mA0l : &mA1l, a_full(sa), ka, m0);
+            }
           }
           __syncwarp();
           ++ia;
@@ -321,8 +340,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mA0h, const __grid_constant__
             const uint32_t dstB = b_ring + sb * 2 * TC_PLANE_BYTES;
             if (elect_one()) {
               mbar_expect_tx(b_full(sb), stage_bytes);
-              tma_load_2d(dstB, &mBh, b_full(sb), kb * TC_BK + b_k, n0 + c * TC_NC);
-              if (p.planes == 2) tma_load_2d(dstB + TC_PLANE_BYTES, &mBl, b_full(sb), kb * TC_BK + b_k, n0 + c * TC_NC);
+              if (p.mn_major) {
+                const int kk = kb * TC_BK + b_k, nn = n0 + c * TC_NC;
+                tma_load_2d(dstB, &mBh, b_full(sb), nn, kk); tma_load_2d(dstB + 8192u, &mBh, b_full(sb), nn + 64, kk);
+                tma_load_2d(dstB + TC_PLANE_BYTES, &mBl, b_full(sb), nn, kk); tma_load_2d(dstB + TC_PLANE_BYTES + 8192u, &mBl, b_full(sb), nn + 64, kk);
+              } else {
+                tma_load_2d(dstB, &mBh, b_full(sb), kb * TC_BK + b_k, n0 + c * TC_NC);
+                if (p.planes == 2) tma_load_2d(dstB + TC_PLANE_BYTES, &mBl, b_full(sb), kb * TC_BK + b_k, n0 + c * TC_NC);
+              }
             }
             __syncwarp();
             ++ib;
@@ -333,7 +358,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mA0h, const __grid_constant__
   } else if (warp == 1) {
     // ================================ MMA issuer ================================
     {
-      const uint32_t idesc = make_idesc_bf16(TC_BM, p.mma_n);
+      const uint32_t idesc = make_idesc_bf16(TC_BM, p.mma_n) | (p.mn_major ? ((1u << 15) | (1u << 16)) : 0u);      // a_major / b_major = MN
       uint32_t ia = 0, ib = 0, it = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
         const uint32_t buf = dbuf ? (it & 1u) : 0u, use = dbuf ? (it >> 1) : it;
@@ -350,12 +375,15 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mA0h, const __grid_constant__
             tc_fence_after();
             const uint32_t bH = b_ring + sb * 2 * TC_PLANE_BYTES, bL = bH + TC_PLANE_BYTES;
             const uint32_t d = tmem_base + 256u * buf + (uint32_t)(c * TC_NC);
-            const uint64_t dAH = make_sw128_desc(aH), dAL = make_sw128_desc(aL), dBH = make_sw128_desc(bH), dBL = make_sw128_desc(bL);
+            const bool mn = p.mn_major != 0;
+            const uint64_t dAH = mn ? make_sw128_desc_mn(aH) : make_sw128_desc(aH), dAL = mn ? make_sw128_desc_mn(aL) : make_sw128_desc(aL);
+            const uint64_t dBH = mn ? make_sw128_desc_mn(bH) : make_sw128_desc(bH), dBL = mn ? make_sw128_desc_mn(bL) : make_sw128_desc(bL);
+            const uint32_t kadv = mn ? 128u : 2u;        // K-major: 16 bf16 = 32 B inside the swizzle atom; MN-major: 16 K rows x 128 B = 2 KB
             if (elect_one()) {
 #pragma unroll
-              for (int ks = 0; ks < TC_BK / 16; ++ks) {  // 16 bf16 = 32 bytes along K inside the swizzle atom: descriptor += 2
-                umma_kstep(d, dAH + 2u * ks, dAL + 2u * ks, dBH + 2u * ks, dBL + 2u * ks, idesc, (kb > 0 || ks > 0) ? 1u : 0u, p.planes == 2);
-                if (p.lolo && p.planes == 2) umma_lolo(d, dAL + 2u * ks, dBL + 2u * ks, idesc);
+              for (int ks = 0; ks < TC_BK / 16; ++ks) {
+                umma_kstep(d, dAH + kadv * ks, dAL + kadv * ks, dBH + kadv * ks, dBL + kadv * ks, idesc, (kb > 0 || ks > 0) ? 1u : 0u, p.planes == 2);
+                if (p.lolo && p.planes == 2) umma_lolo(d, dAL + kadv * ks, dBL + kadv * ks, idesc);
               }
               tc_commit(b_empty(sb));     // frees this weight stage once the MMAs above retire
             }

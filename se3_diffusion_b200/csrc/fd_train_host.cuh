@@ -64,10 +64,11 @@ struct TrainTc {
   char* sarena = nullptr;
   __nv_bfloat16 *s0h = nullptr, *s0l = nullptr, *s1h = nullptr, *s1l = nullptr;    // [E,384], [E,128]
   CUtensorMap m0h, m0l, m1h, m1l;
-  // transposed plane scratch for the weight gradients over the edge rows: dy^T [<=384, Ep], x^T [<=384, Ep], z^T [128, Ep]
+  // weight gradients over the edge rows read the same K-major plane images as MN-major operands (contraction over the rows): second
+  // activation scratch for the x operand (h1 / h2 planes [E,384]) and z's planes [E,128], and {64 channels x 64 rows} box maps of all four
   long long Ep = 0;
-  __nv_bfloat16 *tah = nullptr, *tal = nullptr, *tbh = nullptr, *tbl = nullptr, *tzh = nullptr, *tzl = nullptr;
-  CUtensorMap ma384h, ma384l, ma128h, ma128l, mb384h, mb384l, mb128h, mb128l, mzh, mzl;
+  __nv_bfloat16 *s2h = nullptr, *s2l = nullptr, *s3h = nullptr, *s3l = nullptr;
+  CUtensorMap n0h, n0l, n1h, n1l, n2h, n2l, n3h, n3l;
 };
 
 struct fd_train_state {
@@ -244,20 +245,15 @@ struct TG {
     p.nch = 1; p.num_tiles = p.m_tiles * chunks; p.n_valid = W.rows; p.out_f32 = out; p.ldo = ldo; p.relumask = relumask; p.ldm = ldm;
     if (tc_launch_maps(a0h, a0l, a1h, a1l, W.mh, W.ml, p, st, &h->launches)) err = fail(FD_ECUDA, "training tcgen05 GEMM launch failed: %s", cudaGetErrorString(cudaGetLastError()));
   }
-  // x [M, ld] (first C columns) -> transposed planes [Cp, Ep] (zero padded)
-  void tsplit(const float* x, int ld, long long M, int C, int Cp, long long Ep, __nv_bfloat16* hi, __nv_bfloat16* lo) {
-    if (err) return;
-    tsplit_planes_kernel<<<dim3((unsigned)(Ep / 64), Cp / 32), dim3(32, 8), 0, st>>>(x, ld, M, C, Ep, hi, lo);
-    ck("tsplit_planes");
-  }
-  // dW[Cout][lddw] (first Cin columns) += A^T-planes (Cout rows) x B^T-planes (Cin rows, padded to CinP) contracted over Ep, on tcgen05:
-  // k-slices = inner batches of tc_gemm_kernel's batched mode, partial tiles combined by the atomic fp32 epilogue
-  void tc_wgrad(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh, const CUtensorMap& bl, int Cout, int Cin, int CinP, long long Ep,
-                float* dW, int lddw) {
+  // dW[Cout][lddw] (first Cin columns) += dy^T x on tcgen05, both operands read IN PLACE as MN-major planes [E rows (K), C columns (MN)]
+  // (the K-major images the forward / dgrad GEMMs use): k-slices over the rows = inner batches of tc_gemm_kernel's batched mode, partial
+  // tiles combined by the atomic fp32 epilogue
+  void tc_wgrad(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh, const CUtensorMap& bl, int Cout, int Cin, long long Ep, float* dW,
+                int lddw) {
     if (err) return;
     TcGemmParams p{};
-    p.M = Cout; p.N = CinP; p.planes = 2; p.epi = TC_EPI_F32; p.atomic = 1;
-    p.m_tiles = (Cout + TC_BM - 1) / TC_BM; p.nch = CinP / TC_NC;
+    p.M = Cout; p.N = Cin; p.planes = 2; p.epi = TC_EPI_F32; p.atomic = 1; p.mn_major = 1;
+    p.m_tiles = (Cout + TC_BM - 1) / TC_BM; p.nch = Cin / TC_NC;
     p.bat_tiles = p.m_tiles;
     const long long kb_total = Ep / TC_BK;
     long long slices = h->sm_count / p.bat_tiles;
@@ -316,21 +312,18 @@ static int ttc_ensure_scratch(TrainTc& T, long long E) {
   if (T.sarena) { cudaDeviceSynchronize(); cudaFree(T.sarena); T.sarena = nullptr; }
   const size_t b0 = al256((size_t)E * ET_HID * 2), b1 = al256((size_t)E * C_Z * 2);
   const long long Ep = (E + 63) / 64 * 64;
-  const size_t t3 = al256((size_t)ET_HID * Ep * 2), t1 = al256((size_t)C_Z * Ep * 2);
-  if (cudaMalloc(&T.sarena, 2 * b0 + 2 * b1 + 4 * t3 + 2 * t1) != cudaSuccess) { cudaGetLastError(); return fail(FD_ENOMEM, "training plane scratch allocation failed"); }
+  if (cudaMalloc(&T.sarena, 4 * b0 + 4 * b1) != cudaSuccess) { cudaGetLastError(); return fail(FD_ENOMEM, "training plane scratch allocation failed"); }
   T.E = E; T.Ep = Ep;
   char* p = T.sarena;
   T.s0h = reinterpret_cast<__nv_bfloat16*>(p); p += b0; T.s0l = reinterpret_cast<__nv_bfloat16*>(p); p += b0;
   T.s1h = reinterpret_cast<__nv_bfloat16*>(p); p += b1; T.s1l = reinterpret_cast<__nv_bfloat16*>(p); p += b1;
-  T.tah = reinterpret_cast<__nv_bfloat16*>(p); p += t3; T.tal = reinterpret_cast<__nv_bfloat16*>(p); p += t3;
-  T.tbh = reinterpret_cast<__nv_bfloat16*>(p); p += t3; T.tbl = reinterpret_cast<__nv_bfloat16*>(p); p += t3;
-  T.tzh = reinterpret_cast<__nv_bfloat16*>(p); p += t1; T.tzl = reinterpret_cast<__nv_bfloat16*>(p);
+  T.s2h = reinterpret_cast<__nv_bfloat16*>(p); p += b0; T.s2l = reinterpret_cast<__nv_bfloat16*>(p); p += b0;
+  T.s3h = reinterpret_cast<__nv_bfloat16*>(p); p += b1; T.s3l = reinterpret_cast<__nv_bfloat16*>(p);
   int rc = tc_make_map(&T.m0h, T.s0h, E, ET_HID) | tc_make_map(&T.m0l, T.s0l, E, ET_HID) | tc_make_map(&T.m1h, T.s1h, E, C_Z) |
            tc_make_map(&T.m1l, T.s1l, E, C_Z);
-  rc |= tc_make_map(&T.ma384h, T.tah, ET_HID, Ep) | tc_make_map(&T.ma384l, T.tal, ET_HID, Ep) | tc_make_map(&T.ma128h, T.tah, C_Z, Ep) |
-        tc_make_map(&T.ma128l, T.tal, C_Z, Ep) | tc_make_map(&T.mb384h, T.tbh, ET_HID, Ep) | tc_make_map(&T.mb384l, T.tbl, ET_HID, Ep) |
-        tc_make_map(&T.mb128h, T.tbh, C_Z, Ep) | tc_make_map(&T.mb128l, T.tbl, C_Z, Ep) | tc_make_map(&T.mzh, T.tzh, C_Z, Ep) |
-        tc_make_map(&T.mzl, T.tzl, C_Z, Ep);
+  rc |= tc_make_map(&T.n0h, T.s0h, E, ET_HID, 64) | tc_make_map(&T.n0l, T.s0l, E, ET_HID, 64) | tc_make_map(&T.n1h, T.s1h, E, C_Z, 64) |
+        tc_make_map(&T.n1l, T.s1l, E, C_Z, 64) | tc_make_map(&T.n2h, T.s2h, E, ET_HID, 64) | tc_make_map(&T.n2l, T.s2l, E, ET_HID, 64) |
+        tc_make_map(&T.n3h, T.s3h, E, C_Z, 64) | tc_make_map(&T.n3l, T.s3l, E, C_Z, 64);
   return rc ? fail(FD_ECUDA, "cuTensorMapEncodeTiled failed for the training plane scratch") : FD_OK;
 }
 static void ttc_free(TrainTc& T) {
@@ -693,21 +686,19 @@ static void edge_transition_backward(fd_context* h, TG& f, TrainTape& T, int b, 
     f.dgrad(T.dy128, C_Z, Wf, ET_HID, C_Z, ET_HID, T.dh384a, ET_HID, E, false, X.h2, ET_HID);
   }
   if (f.tc_on()) {
-    // weight gradients over the edge rows on tcgen05: transposed plane images of the two operands, K = E split into k-slices
+    // weight gradients over the edge rows on tcgen05 (MN-major reads of the plane images; s1 = dy, s0 = dh2 / dh1, s2 = h2 / h1, s3 = z)
     TrainTcLayer& L = C.et[b];
-    f.tsplit(T.dy128, C_Z, E, C_Z, C_Z, C.Ep, C.tah, C.tal);                                       // dy^T
-    f.tsplit(X.h2, ET_HID, E, ET_HID, ET_HID, C.Ep, C.tbh, C.tbl);                                 // h2^T
-    f.tsplit(T.z[b], C_Z, E, C_Z, C_Z, C.Ep, C.tzh, C.tzl);                                        // z^T
-    f.tc_wgrad(C.ma128h, C.ma128l, C.mb384h, C.mb384l, C_Z, ET_HID, ET_HID, C.Ep, dWf, ET_HID);    // dWf += dy^T h2
-    f.tc_wgrad(C.ma128h, C.ma128l, C.mzh, C.mzl, C_Z, C_Z, C_Z, C.Ep, dWf, ET_HID);                // dWf[:, :128] += dy^T z
+    f.split(X.h2, ET_HID, E, ET_HID, C.s2h, C.s2l);
+    f.split(T.z[b], C_Z, E, C_Z, C.s3h, C.s3l);
+    f.tc_wgrad(C.n1h, C.n1l, C.n2h, C.n2l, C_Z, ET_HID, C.Ep, dWf, ET_HID);                        // dWf += dy^T h2
+    f.tc_wgrad(C.n1h, C.n1l, C.n3h, C.n3l, C_Z, C_Z, C.Ep, dWf, ET_HID);                           // dWf[:, :128] += dy^T z
     f.bgrad(T.dh384a, ET_HID, E, ET_HID, f.g(p + "trunk.2.bias"));
-    f.tsplit(T.dh384a, ET_HID, E, ET_HID, ET_HID, C.Ep, C.tah, C.tal);                             // dh2^T
-    f.tsplit(X.h1, ET_HID, E, ET_HID, ET_HID, C.Ep, C.tbh, C.tbl);                                 // h1^T
-    f.tc_wgrad(C.ma384h, C.ma384l, C.mb384h, C.mb384l, ET_HID, ET_HID, ET_HID, C.Ep, f.g(p + "trunk.2.weight"), ET_HID);   // dW2 += dh2^T h1
     f.split(T.dh384a, ET_HID, E, ET_HID, C.s0h, C.s0l);
+    f.split(X.h1, ET_HID, E, ET_HID, C.s2h, C.s2l);
+    f.tc_wgrad(C.n0h, C.n0l, C.n2h, C.n2l, ET_HID, ET_HID, C.Ep, f.g(p + "trunk.2.weight"), ET_HID);   // dW2 += dh2^T h1
     f.tc_gemm(C.m0h, C.m0l, 6, C.m0h, C.m0l, 0, L.w2t, E, T.dh384b, ET_HID, nullptr, false, nullptr, 0, 0, N, X.h1, ET_HID);        // dh1 = (dh2 W2) * (h1 > 0)
-    f.tsplit(T.dh384b, ET_HID, E, ET_HID, ET_HID, C.Ep, C.tah, C.tal);                             // dh1^T
-    f.tc_wgrad(C.ma384h, C.ma384l, C.mzh, C.mzl, ET_HID, C_Z, C_Z, C.Ep, dW1, ET_HID);             // dW1[:, :128] += dh1^T z
+    f.split(T.dh384b, ET_HID, E, ET_HID, C.s0h, C.s0l);
+    f.tc_wgrad(C.n0h, C.n0l, C.n3h, C.n3l, ET_HID, C_Z, C.Ep, dW1, ET_HID);                        // dW1[:, :128] += dh1^T z
   } else {
     if (!f.wgrad(T.dy128, C_Z, X.h2, ET_HID, dWf, ET_HID, C_Z, ET_HID, E, 1.f, f.g(p + "final_layer.bias"))) f.bgrad(T.dy128, C_Z, E, C_Z, f.g(p + "final_layer.bias"));
     f.wgrad(T.dy128, C_Z, T.z[b], C_Z, dWf, ET_HID, C_Z, C_Z, E);
@@ -725,8 +716,7 @@ static void edge_transition_backward(fd_context* h, TG& f, TrainTape& T, int b, 
   f.bgrad(T.RS1, ET_HID, R, ET_HID, f.g(p + "trunk.0.bias"));
   f.wgrad(T.RSy, C_Z, X.nb, C_Z, dWf + C_Z, ET_HID, C_Z, C_Z, R);
   f.wgrad(T.CSy, C_Z, X.nb, C_Z, dWf + 2 * C_Z, ET_HID, C_Z, C_Z, R);
-  if (f.tc_on()) {
-    f.split(T.dh384b, ET_HID, E, ET_HID, C.s0h, C.s0l);                                    // s1 still holds dy's planes
+  if (f.tc_on()) {                                                                         // s0 = dh1 planes, s1 = dy planes (above)
     f.tc_gemm(C.m0h, C.m0l, 6, C.m1h, C.m1l, 2, C.et[b].dzw, E, dz_out, C_Z, nullptr, false, nullptr, 0, 0, N, nullptr, 0);    // dz = dh1 W1[:, :128] + dy Wf[:, :128]
   } else {
     f.dgrad(T.dh384b, ET_HID, W1, ET_HID, ET_HID, C_Z, dz_out, C_Z, E);                    // dz = dh1 W1[:, :128]
