@@ -251,6 +251,9 @@ struct TcGemmParams {
   // training path (TC_EPI_F32 only): zero the output where relumask[m][n] <= 0 (backward of a ReLU whose OUTPUT is relumask); `rowadd`
   // (edge-row node terms) is honoured by the fp32 epilogue as well
   const float* relumask; int ldm;
+  // TC_EPI_RELU extension (training backward): the planes written are acc (+bias) WITHOUT the ReLU where maskplane[m][n] != 0 and 0 elsewhere —
+  // d(pre-activation) = d(post-activation) * [activation > 0], the activation given by its bf16 hi plane ([M, N], same layout as the output)
+  const __nv_bfloat16* maskplane;
   int mn_major;                       // both operands are MN-major: planes [K rows, MN columns] (an activation tensor [rows, C] contracted over its
                                       // ROWS — the weight gradient dW = dy^T x — read in place, no transposed copy): TMA boxes {64 MN, 64 K}, two per
                                       // 128-wide tile, UMMA descriptors with LBO = 8 KB (next 64-column block) and SBO = 1 KB (next 8 K rows)
@@ -492,8 +495,15 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mA0h, const __grid_constant__
                 const float4 y = *reinterpret_cast<const float4*>(add_j + c0 + q * 4);
                 bi.x += x.x + y.x; bi.y += x.y + y.y; bi.z += x.z + y.z; bi.w += x.w + y.w;
               }
-              const float v0 = fmaxf(__uint_as_float(r[q * 4 + 0]) + bi.x, 0.f), v1 = fmaxf(__uint_as_float(r[q * 4 + 1]) + bi.y, 0.f);
-              const float v2 = fmaxf(__uint_as_float(r[q * 4 + 2]) + bi.z, 0.f), v3 = fmaxf(__uint_as_float(r[q * 4 + 3]) + bi.w, 0.f);
+              float v0, v1, v2, v3;
+              if (p.maskplane) {
+                const uint2 mk = *reinterpret_cast<const uint2*>(p.maskplane + m * p.N + c0 + q * 4);     // 4 bf16: non-zero <=> activation > 0
+                v0 = (mk.x & 0x00007fffu) ? __uint_as_float(r[q * 4 + 0]) + bi.x : 0.f; v1 = (mk.x & 0x7fff0000u) ? __uint_as_float(r[q * 4 + 1]) + bi.y : 0.f;
+                v2 = (mk.y & 0x00007fffu) ? __uint_as_float(r[q * 4 + 2]) + bi.z : 0.f; v3 = (mk.y & 0x7fff0000u) ? __uint_as_float(r[q * 4 + 3]) + bi.w : 0.f;
+              } else {
+                v0 = fmaxf(__uint_as_float(r[q * 4 + 0]) + bi.x, 0.f); v1 = fmaxf(__uint_as_float(r[q * 4 + 1]) + bi.y, 0.f);
+                v2 = fmaxf(__uint_as_float(r[q * 4 + 2]) + bi.z, 0.f); v3 = fmaxf(__uint_as_float(r[q * 4 + 3]) + bi.w, 0.f);
+              }
               split_bf16(v0, hi[q * 4 + 0], lo[q * 4 + 0]); split_bf16(v1, hi[q * 4 + 1], lo[q * 4 + 1]);
               split_bf16(v2, hi[q * 4 + 2], lo[q * 4 + 2]); split_bf16(v3, hi[q * 4 + 3], lo[q * 4 + 3]);
             }

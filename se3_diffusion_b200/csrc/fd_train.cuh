@@ -84,6 +84,24 @@ __global__ void pack_planes_kernel(const float* __restrict__ src, int ld, int ro
   lo[(long long)r * dst_ld + dst_col0 + c] = l;
 }
 
+// Sums over one residue axis of an edge tensor given as bf16 hi/lo planes [B,N,N,C] (value = hi + lo); same modes as edge_axis_sum_kernel.
+__global__ void __launch_bounds__(128) edge_axis_sum_planes_kernel(const __nv_bfloat16* __restrict__ Xh, const __nv_bfloat16* __restrict__ Xl,
+                                                                   float* __restrict__ out, int N, int C, int mode) {
+  const long long ba = blockIdx.x;
+  const long long b = ba / N; const int a = (int)(ba - b * N);
+  const long long sa = mode == 0 ? (long long)N * C : C, sk = mode == 0 ? C : (long long)N * C;
+  const long long base = b * N * N * C + a * sa;
+  for (int c = threadIdx.x * 2; c < C; c += 256) {          // two channels per thread (one 32-bit load per plane)
+    float s0 = 0.f, s1 = 0.f;
+    for (int k = 0; k < N; ++k) {
+      const uint32_t h = *reinterpret_cast<const uint32_t*>(Xh + base + k * sk + c), l = *reinterpret_cast<const uint32_t*>(Xl + base + k * sk + c);
+      s0 += __uint_as_float(h << 16) + __uint_as_float(l << 16);
+      s1 += __uint_as_float(h & 0xffff0000u) + __uint_as_float(l & 0xffff0000u);
+    }
+    out[ba * C + c] = s0; out[ba * C + c + 1] = s1;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 // LayerNorm backward (torch.nn.LayerNorm, eps 1e-5).  One warp per row, persistent grid; dgamma/dbeta accumulated in registers,
 // reduced per block in shared memory, one atomicAdd per channel per block.

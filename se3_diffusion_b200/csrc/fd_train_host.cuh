@@ -53,7 +53,11 @@ struct TrainTape {
 // linears run on tc_gemm_kernel (fd_tc.cuh: TMA-staged bf16 hi/lo planes, UMMA, TMEM accumulators, fp32 epilogue).  Activations are split
 // into plane scratch right before each GEMM; weight planes (and their transposes for the dgrads) are rebuilt from the fp32 arena each step.
 struct TrainTcMat { __nv_bfloat16 *hi = nullptr, *lo = nullptr; CUtensorMap mh, ml; int rows = 0, cols = 0; };
-struct TrainTcLayer { TrainTcMat w1z, w2, wfx, wft, w2t, dzw; };
+struct TrainTcAct {   // one activation tensor as bf16 hi/lo planes [E, C]: K-major maps (box 64 k x 128 rows) for forward / dgrad, MN-major maps
+                      // (box 64 channels x 64 rows) for the weight gradients
+  __nv_bfloat16 *hi = nullptr, *lo = nullptr; CUtensorMap kh, kl, nh, nl;
+};
+struct TrainTcLayer { TrainTcMat w1z, w2, wfx, wft, w2t, dzw; TrainTcAct ph1, ph2, pz; };
 struct TrainTc {
   bool weights_ready = false;
   char* warena = nullptr;
@@ -68,7 +72,8 @@ struct TrainTc {
   // activation scratch for the x operand (h1 / h2 planes [E,384]) and z's planes [E,128], and {64 channels x 64 rows} box maps of all four
   long long Ep = 0;
   __nv_bfloat16 *s2h = nullptr, *s2l = nullptr, *s3h = nullptr, *s3l = nullptr;
-  CUtensorMap n0h, n0l, n1h, n1l, n2h, n2l, n3h, n3l;
+  CUtensorMap n0h, n0l, n1h, n1l, n2h, n2l, n3h, n3l, m2h, m2l;
+  char* parena = nullptr;          // per-layer persistent planes of h1, h2 [E,384] and z [E,128] (written by the forward, read by the backward)
 };
 
 struct fd_train_state {
@@ -245,6 +250,21 @@ struct TG {
     p.nch = 1; p.num_tiles = p.m_tiles * chunks; p.n_valid = W.rows; p.out_f32 = out; p.ldo = ldo; p.relumask = relumask; p.ldm = ldm;
     if (tc_launch_maps(a0h, a0l, a1h, a1l, W.mh, W.ml, p, st, &h->launches)) err = fail(FD_ECUDA, "training tcgen05 GEMM launch failed: %s", cudaGetErrorString(cudaGetLastError()));
   }
+  // planes out[M, W.rows] = relu([A0 | A1] W^T + bias + node terms), or — with `mask` — ([A0 | A1] W^T) where mask != 0 and 0 elsewhere (the
+  // backward of that ReLU): tc_gemm_kernel's plane-writing epilogue, the edge activations never exist in fp32
+  void tc_gemm_planes(const CUtensorMap& a0h, const CUtensorMap& a0l, int KB0, const TrainTcMat& W, long long M, __nv_bfloat16* out_hi, __nv_bfloat16* out_lo,
+                      const float* bias, const float* rowadd, int off_i, int off_j, int nres, const __nv_bfloat16* mask) {
+    if (err) return;
+    TcGemmParams p{};
+    p.M = (int)M; p.N = W.rows; p.KB0 = KB0; p.KB1 = 0; p.planes = 2; p.epi = TC_EPI_RELU; p.bias = bias;
+    p.rowadd = rowadd; p.off_i = off_i; p.off_j = off_j; p.ld_rowadd = ET_NODE; p.nres = nres; p.out_hi = out_hi; p.out_lo = out_lo; p.maskplane = mask;
+    if (tc_launch_maps(a0h, a0l, a0h, a0l, W.mh, W.ml, p, st, &h->launches)) err = fail(FD_ECUDA, "training tcgen05 GEMM (planes) launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+  }
+  void axis_sum_planes(const __nv_bfloat16* hi, const __nv_bfloat16* lo, float* out, long long R, int N, int Cc, int mode) {
+    if (err) return;
+    edge_axis_sum_planes_kernel<<<(unsigned)R, 128, 0, st>>>(hi, lo, out, N, Cc, mode);
+    ck("edge_axis_sum_planes");
+  }
   // dW[Cout][lddw] (first Cin columns) += dy^T x on tcgen05, both operands read IN PLACE as MN-major planes [E rows (K), C columns (MN)]
   // (the K-major images the forward / dgrad GEMMs use): k-slices over the rows = inner batches of tc_gemm_kernel's batched mode, partial
   // tiles combined by the atomic fp32 epilogue
@@ -320,13 +340,24 @@ static int ttc_ensure_scratch(TrainTc& T, long long E) {
   T.s2h = reinterpret_cast<__nv_bfloat16*>(p); p += b0; T.s2l = reinterpret_cast<__nv_bfloat16*>(p); p += b0;
   T.s3h = reinterpret_cast<__nv_bfloat16*>(p); p += b1; T.s3l = reinterpret_cast<__nv_bfloat16*>(p);
   int rc = tc_make_map(&T.m0h, T.s0h, E, ET_HID) | tc_make_map(&T.m0l, T.s0l, E, ET_HID) | tc_make_map(&T.m1h, T.s1h, E, C_Z) |
-           tc_make_map(&T.m1l, T.s1l, E, C_Z);
+           tc_make_map(&T.m1l, T.s1l, E, C_Z) | tc_make_map(&T.m2h, T.s2h, E, ET_HID) | tc_make_map(&T.m2l, T.s2l, E, ET_HID);
+  {
+    if (T.parena) { cudaFree(T.parena); T.parena = nullptr; }
+    if (cudaMalloc(&T.parena, (size_t)(NBLK - 1) * (4 * b0 + 2 * b1)) != cudaSuccess) { cudaGetLastError(); return fail(FD_ENOMEM, "training activation planes allocation failed"); }
+    char* q = T.parena;
+    auto carve = [&](TrainTcAct& a, int Cc, size_t bytes) {
+      a.hi = reinterpret_cast<__nv_bfloat16*>(q); q += bytes; a.lo = reinterpret_cast<__nv_bfloat16*>(q); q += bytes;
+      return tc_make_map(&a.kh, a.hi, E, Cc) | tc_make_map(&a.kl, a.lo, E, Cc) | tc_make_map(&a.nh, a.hi, E, Cc, 64) | tc_make_map(&a.nl, a.lo, E, Cc, 64);
+    };
+    for (int l = 0; l < NBLK - 1; ++l) { rc |= carve(T.et[l].ph1, ET_HID, b0); rc |= carve(T.et[l].ph2, ET_HID, b0); rc |= carve(T.et[l].pz, C_Z, b1); }
+  }
   rc |= tc_make_map(&T.n0h, T.s0h, E, ET_HID, 64) | tc_make_map(&T.n0l, T.s0l, E, ET_HID, 64) | tc_make_map(&T.n1h, T.s1h, E, C_Z, 64) |
         tc_make_map(&T.n1l, T.s1l, E, C_Z, 64) | tc_make_map(&T.n2h, T.s2h, E, ET_HID, 64) | tc_make_map(&T.n2l, T.s2l, E, ET_HID, 64) |
         tc_make_map(&T.n3h, T.s3h, E, C_Z, 64) | tc_make_map(&T.n3l, T.s3l, E, C_Z, 64);
   return rc ? fail(FD_ECUDA, "cuTensorMapEncodeTiled failed for the training plane scratch") : FD_OK;
 }
 static void ttc_free(TrainTc& T) {
+  if (T.parena) cudaFree(T.parena);
   if (T.warena) cudaFree(T.warena);
   if (T.sarena) cudaFree(T.sarena);
   T = TrainTc();
@@ -491,13 +522,11 @@ static int train_forward_impl(fd_context* h, fd_train_state* S, int B, int N, co
       f.lin(X.nb, C_Z, Wf + C_Z, ET_HID, f.w(p + "final_layer.bias"), C_Z, C_Z, X.pquv + 2 * ET_HID, ET_NODE, R);          // U_i (+ bf)
       f.lin(X.nb, C_Z, Wf + 2 * C_Z, ET_HID, nullptr, C_Z, C_Z, X.pquv + 2 * ET_HID + C_Z, ET_NODE, R);                   // V_j
       if (f.tc_on()) {
-        TrainTcLayer& L = C.et[b];
-        f.split(T.z[b], C_Z, E, C_Z, C.s1h, C.s1l);
-        f.tc_gemm(C.m1h, C.m1l, 2, C.m1h, C.m1l, 0, L.w1z, E, X.h1, ET_HID, nullptr, true, X.pquv, 0, ET_HID, N, nullptr, 0);               // h1
-        f.split(X.h1, ET_HID, E, ET_HID, C.s0h, C.s0l);
-        f.tc_gemm(C.m0h, C.m0l, 6, C.m0h, C.m0l, 0, L.w2, E, X.h2, ET_HID, f.w(p + "trunk.2.bias"), true, nullptr, 0, 0, N, nullptr, 0);     // h2
-        f.split(X.h2, ET_HID, E, ET_HID, C.s0h, C.s0l);
-        f.tc_gemm(C.m0h, C.m0l, 6, C.m1h, C.m1l, 2, L.wfx, E, X.ety, C_Z, nullptr, false, X.pquv, 2 * ET_HID, 2 * ET_HID + C_Z, N, nullptr, 0);   // y
+        TrainTcLayer& L = C.et[b];      // h1, h2 exist only as bf16 hi/lo planes (kept for the backward); z's planes are kept as well
+        f.split(T.z[b], C_Z, E, C_Z, L.pz.hi, L.pz.lo);
+        f.tc_gemm_planes(L.pz.kh, L.pz.kl, 2, L.w1z, E, L.ph1.hi, L.ph1.lo, nullptr, X.pquv, 0, ET_HID, N, nullptr);                       // h1
+        f.tc_gemm_planes(L.ph1.kh, L.ph1.kl, 6, L.w2, E, L.ph2.hi, L.ph2.lo, f.w(p + "trunk.2.bias"), nullptr, 0, 0, N, nullptr);           // h2
+        f.tc_gemm(L.ph2.kh, L.ph2.kl, 6, L.pz.kh, L.pz.kl, 2, L.wfx, E, X.ety, C_Z, nullptr, false, X.pquv, 2 * ET_HID, 2 * ET_HID + C_Z, N, nullptr, 0);   // y
       } else {
       GemmArgs g;   // h1 = relu(z W1z^T + P_i + Q_j)
       g.A = T.z[b]; g.lda = C_Z; g.B = W1; g.ldb = ET_HID; g.C = X.h1; g.ldc = ET_HID; g.M = (int)E; g.N = ET_HID; g.K = C_Z; g.relu = 1;
@@ -681,24 +710,20 @@ static void edge_transition_backward(fd_context* h, TG& f, TrainTape& T, int b, 
   if (f.tc_on()) {
     TrainTcLayer& L = C.et[b];
     f.split(T.dy128, C_Z, E, C_Z, C.s1h, C.s1l);
-    f.tc_gemm(C.m1h, C.m1l, 2, C.m1h, C.m1l, 0, L.wft, E, T.dh384a, ET_HID, nullptr, false, nullptr, 0, 0, N, X.h2, ET_HID);        // dh2 = (dy Wf) * (h2 > 0)
+    f.tc_gemm_planes(C.m1h, C.m1l, 2, L.wft, E, C.s0h, C.s0l, nullptr, nullptr, 0, 0, N, L.ph2.hi);                  // dh2 = (dy Wf) * (h2 > 0) -> planes s0
   } else {
     f.dgrad(T.dy128, C_Z, Wf, ET_HID, C_Z, ET_HID, T.dh384a, ET_HID, E, false, X.h2, ET_HID);
   }
   if (f.tc_on()) {
-    // weight gradients over the edge rows on tcgen05 (MN-major reads of the plane images; s1 = dy, s0 = dh2 / dh1, s2 = h2 / h1, s3 = z)
+    // weight gradients over the edge rows on tcgen05: MN-major reads of the plane images (s1 = dy, s0 = dh2, s2 = dh1; h1, h2, z from the forward)
     TrainTcLayer& L = C.et[b];
-    f.split(X.h2, ET_HID, E, ET_HID, C.s2h, C.s2l);
-    f.split(T.z[b], C_Z, E, C_Z, C.s3h, C.s3l);
-    f.tc_wgrad(C.n1h, C.n1l, C.n2h, C.n2l, C_Z, ET_HID, C.Ep, dWf, ET_HID);                        // dWf += dy^T h2
-    f.tc_wgrad(C.n1h, C.n1l, C.n3h, C.n3l, C_Z, C_Z, C.Ep, dWf, ET_HID);                           // dWf[:, :128] += dy^T z
-    f.bgrad(T.dh384a, ET_HID, E, ET_HID, f.g(p + "trunk.2.bias"));
-    f.split(T.dh384a, ET_HID, E, ET_HID, C.s0h, C.s0l);
-    f.split(X.h1, ET_HID, E, ET_HID, C.s2h, C.s2l);
-    f.tc_wgrad(C.n0h, C.n0l, C.n2h, C.n2l, ET_HID, ET_HID, C.Ep, f.g(p + "trunk.2.weight"), ET_HID);   // dW2 += dh2^T h1
-    f.tc_gemm(C.m0h, C.m0l, 6, C.m0h, C.m0l, 0, L.w2t, E, T.dh384b, ET_HID, nullptr, false, nullptr, 0, 0, N, X.h1, ET_HID);        // dh1 = (dh2 W2) * (h1 > 0)
-    f.split(T.dh384b, ET_HID, E, ET_HID, C.s0h, C.s0l);
-    f.tc_wgrad(C.n0h, C.n0l, C.n3h, C.n3l, ET_HID, C_Z, C.Ep, dW1, ET_HID);                        // dW1[:, :128] += dh1^T z
+    f.tc_wgrad(C.n1h, C.n1l, L.ph2.nh, L.ph2.nl, C_Z, ET_HID, C.Ep, dWf, ET_HID);                  // dWf += dy^T h2
+    f.tc_wgrad(C.n1h, C.n1l, L.pz.nh, L.pz.nl, C_Z, C_Z, C.Ep, dWf, ET_HID);                       // dWf[:, :128] += dy^T z
+    f.axis_sum_planes(C.s0h, C.s0l, T.RS1, R, N, ET_HID, 0);
+    f.bgrad(T.RS1, ET_HID, R, ET_HID, f.g(p + "trunk.2.bias"));                                    // sum over the edges of dh2
+    f.tc_wgrad(C.n0h, C.n0l, L.ph1.nh, L.ph1.nl, ET_HID, ET_HID, C.Ep, f.g(p + "trunk.2.weight"), ET_HID);   // dW2 += dh2^T h1
+    f.tc_gemm_planes(C.m0h, C.m0l, 6, L.w2t, E, C.s2h, C.s2l, nullptr, nullptr, 0, 0, N, L.ph1.hi);          // dh1 = (dh2 W2) * (h1 > 0) -> planes s2
+    f.tc_wgrad(C.n2h, C.n2l, L.pz.nh, L.pz.nl, ET_HID, C_Z, C.Ep, dW1, ET_HID);                    // dW1[:, :128] += dh1^T z
   } else {
     if (!f.wgrad(T.dy128, C_Z, X.h2, ET_HID, dWf, ET_HID, C_Z, ET_HID, E, 1.f, f.g(p + "final_layer.bias"))) f.bgrad(T.dy128, C_Z, E, C_Z, f.g(p + "final_layer.bias"));
     f.wgrad(T.dy128, C_Z, T.z[b], C_Z, dWf, ET_HID, C_Z, C_Z, E);
@@ -707,8 +732,13 @@ static void edge_transition_backward(fd_context* h, TG& f, TrainTape& T, int b, 
   if (f.err) return;
   edge_axis_sum_kernel<<<(unsigned)R, 128, 0, st>>>(T.dy128, T.RSy, N, C_Z, 0); f.ck("edge_axis_sum");
   edge_axis_sum_kernel<<<(unsigned)R, 128, 0, st>>>(T.dy128, T.CSy, N, C_Z, 1); f.ck("edge_axis_sum");
-  edge_axis_sum_kernel<<<(unsigned)R, 128, 0, st>>>(T.dh384b, T.RS1, N, ET_HID, 0); f.ck("edge_axis_sum");
-  edge_axis_sum_kernel<<<(unsigned)R, 128, 0, st>>>(T.dh384b, T.CS1, N, ET_HID, 1); f.ck("edge_axis_sum");
+  if (f.tc_on()) {
+    f.axis_sum_planes(C.s2h, C.s2l, T.RS1, R, N, ET_HID, 0);
+    f.axis_sum_planes(C.s2h, C.s2l, T.CS1, R, N, ET_HID, 1);
+  } else {
+    edge_axis_sum_kernel<<<(unsigned)R, 128, 0, st>>>(T.dh384b, T.RS1, N, ET_HID, 0); f.ck("edge_axis_sum");
+    edge_axis_sum_kernel<<<(unsigned)R, 128, 0, st>>>(T.dh384b, T.CS1, N, ET_HID, 1); f.ck("edge_axis_sum");
+  }
   if (!f.tc_on()) f.wgrad(T.dh384b, ET_HID, T.z[b], C_Z, dW1, ET_HID, ET_HID, C_Z, E);
   else f.bgrad(T.RSy, C_Z, R, C_Z, f.g(p + "final_layer.bias"));                                  // sum over the edges = sum over i of the row sums
   f.wgrad(T.RS1, ET_HID, X.nb, C_Z, dW1 + C_Z, ET_HID, ET_HID, C_Z, R);
@@ -716,8 +746,8 @@ static void edge_transition_backward(fd_context* h, TG& f, TrainTape& T, int b, 
   f.bgrad(T.RS1, ET_HID, R, ET_HID, f.g(p + "trunk.0.bias"));
   f.wgrad(T.RSy, C_Z, X.nb, C_Z, dWf + C_Z, ET_HID, C_Z, C_Z, R);
   f.wgrad(T.CSy, C_Z, X.nb, C_Z, dWf + 2 * C_Z, ET_HID, C_Z, C_Z, R);
-  if (f.tc_on()) {                                                                         // s0 = dh1 planes, s1 = dy planes (above)
-    f.tc_gemm(C.m0h, C.m0l, 6, C.m1h, C.m1l, 2, C.et[b].dzw, E, dz_out, C_Z, nullptr, false, nullptr, 0, 0, N, nullptr, 0);    // dz = dh1 W1[:, :128] + dy Wf[:, :128]
+  if (f.tc_on()) {                                                                         // s2 = dh1 planes, s1 = dy planes (above)
+    f.tc_gemm(C.m2h, C.m2l, 6, C.m1h, C.m1l, 2, C.et[b].dzw, E, dz_out, C_Z, nullptr, false, nullptr, 0, 0, N, nullptr, 0);    // dz = dh1 W1[:, :128] + dy Wf[:, :128]
   } else {
     f.dgrad(T.dh384b, ET_HID, W1, ET_HID, ET_HID, C_Z, dz_out, C_Z, E);                    // dz = dh1 W1[:, :128]
     f.dgrad(T.dy128, C_Z, Wf, ET_HID, C_Z, C_Z, dz_out, C_Z, E, true);                     //    + dy Wf[:, :128]
