@@ -262,7 +262,8 @@ inline int mm3_init() {
 // Same contract as launch_gemm.  Small problems stay on the CUDA-core kernel (launch-latency bound anyway).
 inline cudaError_t launch_gemm_mm3(GemmArgs g, bool b_kmajor, cudaStream_t st, bool a_kmajor = true) {
   const double work = 2.0 * g.M * g.N * (double)g.K * g.nb0 * g.nb1;
-  if (work < 3.0e7 || g.M < 32 || g.N < 16 || (!a_kmajor && b_kmajor) || mm3_init()) return launch_gemm(g, b_kmajor, st, a_kmajor);
+  // (weight-gradient form: even an 8-row output — d linear_b — is worth a tensor-core tile when K is the edge count)
+  if (work < 3.0e7 || g.M < (a_kmajor ? 32 : 8) || g.N < 16 || (!a_kmajor && b_kmajor) || mm3_init()) return launch_gemm(g, b_kmajor, st, a_kmajor);
   auto al4 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
   g.vecA = al4(g.A) && g.lda % 4 == 0 && g.sA0 % 4 == 0 && g.sA1 % 4 == 0;
   g.vecB = al4(g.B) && g.ldb % 4 == 0 && g.sB0 % 4 == 0 && g.sB1 % 4 == 0;

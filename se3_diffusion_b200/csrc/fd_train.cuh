@@ -46,6 +46,23 @@ __global__ void __launch_bounds__(128) colsum_kernel(const float* __restrict__ X
   if (m < m1) s0 += X[m * ld + n];
   atomicAdd(out + n, s0 + s1);
 }
+// narrow tensors ([M, N] dense with N | 128, e.g. the [E, 8] pair-bias gradient): viewed as [M*N/128, 128] so that all 128 threads of a block
+// work, the 128 partial columns folded onto the N outputs by the last stage
+__global__ void colsum_fold_kernel(const float* __restrict__ tmp128, int N, float* __restrict__ out) {
+  const int n = threadIdx.x;
+  if (n >= N) return;
+  float s = 0.f;
+  for (int k = n; k < 128; k += N) s += tmp128[k];
+  atomicAdd(out + n, s);
+}
+inline cudaError_t launch_colsum(const float* X, int ld, long long M, int N, float* out, cudaStream_t st);
+inline cudaError_t launch_colsum_narrow(const float* X, long long M, int N, float* out, float* tmp128, cudaStream_t st) {
+  cudaMemsetAsync(tmp128, 0, 128 * sizeof(float), st);
+  cudaError_t e = launch_colsum(X, 128, M * N / 128, 128, tmp128, st);
+  if (e != cudaSuccess) return e;
+  colsum_fold_kernel<<<1, 128, 0, st>>>(tmp128, N, out);
+  return cudaGetLastError();
+}
 inline cudaError_t launch_colsum(const float* X, int ld, long long M, int N, float* out, cudaStream_t st) {
   int slabs = (int)min((long long)1024, max((long long)1, M / 256));
   colsum_kernel<<<dim3((N + 127) / 128, slabs), 128, 0, st>>>(X, ld, M, N, out);

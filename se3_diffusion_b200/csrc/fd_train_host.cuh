@@ -108,7 +108,7 @@ static int ensure_tape(fd_context* h, TrainTape& T, int B, int N) {
       {&T.d320c, R * TF_D}, {&T.dqkv, R * 3 * TF_D}, {&T.dP, PT}, {&T.dfeats, R * IPA_FEAT}, {&T.dproj, R * PROJ_ALL}, {&T.dquat, R * 4},
       {&T.dtrans, R * 3}, {&T.dzA, E * C_Z}, {&T.dzB, E * C_Z}, {&T.dh384a, E * ET_HID}, {&T.dh384b, E * ET_HID}, {&T.dy128, E * C_Z}, {&T.dA, AT},
       {&T.dbias, E * H}, {&T.dzbar, R * H * C_Z}, {&T.Gq, R * H * PQ * 3}, {&T.Gk, R * H * PQ * 3}, {&T.dvp, R * H * PV * 3},
-      {&T.doptg, R * H * PV * 3}, {&T.colsum, (size_t)B * H * N}, {&T.dgamma, 64}, {&T.RS1, R * ET_HID}, {&T.CS1, R * ET_HID}, {&T.RSy, R * C_Z},
+      {&T.doptg, R * H * PV * 3}, {&T.colsum, (size_t)B * H * N}, {&T.dgamma, 64 + 128}, {&T.RS1, R * ET_HID}, {&T.CS1, R * ET_HID}, {&T.RSy, R * C_Z},
       {&T.CSy, R * C_Z}, {&T.dnb, R * C_Z}, {&T.dee, E * C_Z}};
   for (int b = 0; b < NBLK; ++b) {
     TBlockTape& X = T.blk[b];
@@ -142,6 +142,7 @@ static int ensure_tape(fd_context* h, TrainTape& T, int B, int N) {
 // ---- launch helpers ------------------------------------------------------------------------------------------------------------
 struct TG {
   fd_context* h; cudaStream_t st; const float* P; float* G;
+  float* T_tmp128 = nullptr;       // 128-float scratch of the narrow column sums
   int err = 0;
   const float* w(const std::string& n) const { return P + arena_layout().off[arena_layout().index.at(n)]; }
   float* g(const std::string& n) const { return G + arena_layout().off[arena_layout().index.at(n)]; }
@@ -194,7 +195,8 @@ struct TG {
   }
   void bgrad(const float* dy, int lddy, long long rows, int Nout, float* db) {
     if (err) return;
-    cudaError_t e = launch_colsum(dy, lddy, rows, Nout, db, st);
+    const bool narrow = Nout < 64 && lddy == Nout && 128 % Nout == 0 && (rows * Nout) % 128 == 0 && rows >= 4096;
+    cudaError_t e = narrow ? launch_colsum_narrow(dy, rows, Nout, db, T_tmp128, st) : launch_colsum(dy, lddy, rows, Nout, db, st);
     h->launches++;
     if (e != cudaSuccess) err = fail(FD_ECUDA, "colsum launch failed: %s", cudaGetErrorString(e));
   }
@@ -763,6 +765,7 @@ static int train_backward_impl(fd_context* h, fd_train_state* S, const fd_train_
   TrainTape& T = S->tape;
   if (!T.valid) return fail(FD_ESTATE, "fd_train_backward: no training forward on tape");
   TG f{h, st, S->P, S->G};
+  f.T_tmp128 = T.dgamma + 64;
   const long long R = T.rows, E = T.edges;
   const int N = T.N;
   const float* res_mask = T.res_mask;
