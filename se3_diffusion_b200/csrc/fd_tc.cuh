@@ -261,6 +261,69 @@ struct TcGemmParams {
                                       // the batched mode's inner batches with o_s1 = 0); bias / relu / mask / residual are ignored
 };
 
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&r)[32]);
+__device__ __forceinline__ void tmem_ld_wait();
+
+// Coalesced plane I/O for the plane-writing epilogues: a warp owns 32 consecutive rows, each thread one row.  64 bf16 columns (128 B) of
+// every row go through a 4 KB XOR-swizzled shared-memory tile so that each global instruction moves four whole 128-byte row segments
+// (row-per-thread 16-byte accesses touch 32 different rows per instruction: half-used sectors, 8x the LSU wavefronts).  `ldn` = row stride.
+__device__ __forceinline__ void warp_store_rows64_ld(uint32_t stage, const uint32_t (&w)[32], __nv_bfloat16* out, long long m_warp, int col0,
+                                                     long long M, int lane, int ldn) {
+#pragma unroll
+  for (int u = 0; u < 8; ++u)
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage + (uint32_t)(lane * 128 + ((u ^ (lane & 7)) << 4))), "r"(w[4 * u]),
+                 "r"(w[4 * u + 1]), "r"(w[4 * u + 2]), "r"(w[4 * u + 3])
+                 : "memory");
+  __syncwarp();
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int r = k * 4 + (lane >> 3), u = lane & 7;
+    uint4 val;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(val.x), "=r"(val.y), "=r"(val.z), "=r"(val.w)
+                 : "r"(stage + (uint32_t)(r * 128 + ((u ^ (r & 7)) << 4))) : "memory");
+    if (m_warp + r < M) *reinterpret_cast<uint4*>(out + (m_warp + r) * ldn + col0 + u * 8) = val;
+  }
+  __syncwarp();
+}
+// fp32 variant: 32 fp32 columns (128 B) of every row; `out` already points at the first of those columns of row 0
+__device__ __forceinline__ void warp_store_rows32f(uint32_t stage, const uint32_t (&w)[32], float* out, long long m_warp, long long M, int lane,
+                                                   long long ldo) {
+#pragma unroll
+  for (int u = 0; u < 8; ++u)
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage + (uint32_t)(lane * 128 + ((u ^ (lane & 7)) << 4))), "r"(w[4 * u]),
+                 "r"(w[4 * u + 1]), "r"(w[4 * u + 2]), "r"(w[4 * u + 3])
+                 : "memory");
+  __syncwarp();
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int r = k * 4 + (lane >> 3), u = lane & 7;
+    uint4 val;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(val.x), "=r"(val.y), "=r"(val.z), "=r"(val.w)
+                 : "r"(stage + (uint32_t)(r * 128 + ((u ^ (r & 7)) << 4))) : "memory");
+    if (m_warp + r < M) *reinterpret_cast<uint4*>(out + (m_warp + r) * ldo + u * 4) = val;
+  }
+  __syncwarp();
+}
+// the inverse: 64 bf16 columns of the warp's 32 rows, global -> (swizzled smem) -> each thread's own row in registers
+__device__ __forceinline__ void warp_load_rows64_ld(uint32_t stage, uint32_t (&w)[32], const __nv_bfloat16* in, long long m_warp, int col0,
+                                                    long long M, int lane, int ldn) {
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int r = k * 4 + (lane >> 3), u = lane & 7;
+    uint4 val = make_uint4(0u, 0u, 0u, 0u);
+    if (m_warp + r < M) val = *reinterpret_cast<const uint4*>(in + (m_warp + r) * ldn + col0 + u * 8);
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage + (uint32_t)(r * 128 + ((u ^ (r & 7)) << 4))), "r"(val.x), "r"(val.y),
+                 "r"(val.z), "r"(val.w)
+                 : "memory");
+  }
+  __syncwarp();
+#pragma unroll
+  for (int u = 0; u < 8; ++u)
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w[4 * u]), "=r"(w[4 * u + 1]), "=r"(w[4 * u + 2]), "=r"(w[4 * u + 3])
+                 : "r"(stage + (uint32_t)(lane * 128 + ((u ^ (lane & 7)) << 4))) : "memory");
+  __syncwarp();
+}
+
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap mA0h, const __grid_constant__ CUtensorMap mA0l,
                const __grid_constant__ CUtensorMap mA1h, const __grid_constant__ CUtensorMap mA1l,
@@ -454,68 +517,84 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mA0h, const __grid_constant__
           }
           uint32_t r[32];
           tmem_ld32(trow + (uint32_t)c0, r);
-          if (act && p.atomic) {
-            float* orow = p.out_f32 + o_off + m * p.ldo + n;
-            const float al = p.alpha != 0.f ? p.alpha : 1.f;
+          if (p.atomic) {                     // warp-uniform
+            if (act) {
+              float* orow = p.out_f32 + o_off + m * p.ldo + n;
+              const float al = p.alpha != 0.f ? p.alpha : 1.f;
 #pragma unroll
-            for (int q = 0; q < 32; ++q)
-              if (n + q < p.n_valid) atomicAdd(orow + q, al * __uint_as_float(r[q]));
-          } else if (act) {
-            float* orow = p.out_f32 + o_off + m * p.ldo + n;
+              for (int q = 0; q < 32; ++q)
+                if (n + q < p.n_valid) atomicAdd(orow + q, al * __uint_as_float(r[q]));
+            }
+          } else {
+            // full 32-column groups leave through the warp's staging tile (whole 128-byte row segments per store instruction); a ragged last
+            // group is stored row-per-thread
+            const bool full = n + 32 <= p.n_valid && (p.ldo & 3) == 0 && (o_off & 3) == 0;        // warp-uniform
+            uint32_t wv[32];
+            if (act) {
+              float* orow = p.out_f32 + o_off + m * p.ldo + n;
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              if (n + q * 4 < p.n_valid) {
-                float4 v = make_float4(__uint_as_float(r[q * 4 + 0]), __uint_as_float(r[q * 4 + 1]), __uint_as_float(r[q * 4 + 2]), __uint_as_float(r[q * 4 + 3]));
-                if (p.alpha != 0.f) { v.x *= p.alpha; v.y *= p.alpha; v.z *= p.alpha; v.w *= p.alpha; }
-                v.x += bv[q].x; v.y += bv[q].y; v.z += bv[q].z; v.w += bv[q].w;
-                if (p.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-                v.x *= rm; v.y *= rm; v.z *= rm; v.w *= rm;
-                v.x += rv[q].x; v.y += rv[q].y; v.z += rv[q].z; v.w += rv[q].w;
-                if (p.relumask) {
-                  const float4 mk = *reinterpret_cast<const float4*>(p.relumask + m * p.ldm + n + q * 4);
-                  v.x = mk.x > 0.f ? v.x : 0.f; v.y = mk.y > 0.f ? v.y : 0.f; v.z = mk.z > 0.f ? v.z : 0.f; v.w = mk.w > 0.f ? v.w : 0.f;
+              for (int q = 0; q < 8; ++q) {
+                if (n + q * 4 < p.n_valid) {
+                  float4 v = make_float4(__uint_as_float(r[q * 4 + 0]), __uint_as_float(r[q * 4 + 1]), __uint_as_float(r[q * 4 + 2]), __uint_as_float(r[q * 4 + 3]));
+                  if (p.alpha != 0.f) { v.x *= p.alpha; v.y *= p.alpha; v.z *= p.alpha; v.w *= p.alpha; }
+                  v.x += bv[q].x; v.y += bv[q].y; v.z += bv[q].z; v.w += bv[q].w;
+                  if (p.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+                  v.x *= rm; v.y *= rm; v.z *= rm; v.w *= rm;
+                  v.x += rv[q].x; v.y += rv[q].y; v.z += rv[q].z; v.w += rv[q].w;
+                  if (p.relumask) {
+                    const float4 mk = *reinterpret_cast<const float4*>(p.relumask + m * p.ldm + n + q * 4);
+                    v.x = mk.x > 0.f ? v.x : 0.f; v.y = mk.y > 0.f ? v.y : 0.f; v.z = mk.z > 0.f ? v.z : 0.f; v.w = mk.w > 0.f ? v.w : 0.f;
+                  }
+                  if (full) {
+                    wv[q * 4 + 0] = __float_as_uint(v.x); wv[q * 4 + 1] = __float_as_uint(v.y); wv[q * 4 + 2] = __float_as_uint(v.z); wv[q * 4 + 3] = __float_as_uint(v.w);
+                  } else {
+                    *reinterpret_cast<float4*>(orow + q * 4) = v;
+                  }
                 }
-                *reinterpret_cast<float4*>(orow + q * 4) = v;
               }
             }
+            if (full) warp_store_rows32f(bar0 + 1024u + (uint32_t)(warp - 2) * 4096u, wv, p.out_f32 + o_off + n, m - lane, p.M, lane, p.ldo);
           }
         }
       } else if (p.epi == TC_EPI_RELU) {
-        for (int c0 = 0; c0 < p.N; c0 += 32) {
-          uint32_t r[32];
-          tmem_ld32(trow + (uint32_t)c0, r);
-          if (valid) {
-            __align__(16) __nv_bfloat16 hi[32];
-            __align__(16) __nv_bfloat16 lo[32];
+        // 64 columns per step: accumulator -> (+bias, +node terms) -> ReLU or ReLU-mask -> bf16 hi/lo -> coalesced stores through the warp's staging tile
+        const uint32_t stage = bar0 + 1024u + (uint32_t)(warp - 2) * 4096u;
+        const long long m_warp = m - lane;
+        for (int c0 = 0; c0 < p.N; c0 += 64) {
+          uint32_t r0[32], r1[32];
+          tmem_ld32_nowait(trow + (uint32_t)c0, r0);
+          tmem_ld32_nowait(trow + (uint32_t)(c0 + 32), r1);
+          uint32_t mk[32];
+          if (p.maskplane) warp_load_rows64_ld(stage, mk, p.maskplane, m_warp, c0, p.M, lane, p.N);
+          tmem_ld_wait();
+          uint32_t hw[32], lw[32];
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
-              float4 bi = p.bias ? *reinterpret_cast<const float4*>(p.bias + c0 + q * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+              const int cc = c0 + half * 32 + q * 4;
+              float4 bi = (valid && p.bias) ? *reinterpret_cast<const float4*>(p.bias + cc) : make_float4(0.f, 0.f, 0.f, 0.f);
               if (add_i) {
-                const float4 x = *reinterpret_cast<const float4*>(add_i + c0 + q * 4);
-                const float4 y = *reinterpret_cast<const float4*>(add_j + c0 + q * 4);
+                const float4 x = *reinterpret_cast<const float4*>(add_i + cc);
+                const float4 y = *reinterpret_cast<const float4*>(add_j + cc);
                 bi.x += x.x + y.x; bi.y += x.y + y.y; bi.z += x.z + y.z; bi.w += x.w + y.w;
               }
-              float v0, v1, v2, v3;
-              if (p.maskplane) {
-                const uint2 mk = *reinterpret_cast<const uint2*>(p.maskplane + m * p.N + c0 + q * 4);     // 4 bf16: non-zero <=> activation > 0
-                v0 = (mk.x & 0x00007fffu) ? __uint_as_float(r[q * 4 + 0]) + bi.x : 0.f; v1 = (mk.x & 0x7fff0000u) ? __uint_as_float(r[q * 4 + 1]) + bi.y : 0.f;
-                v2 = (mk.y & 0x00007fffu) ? __uint_as_float(r[q * 4 + 2]) + bi.z : 0.f; v3 = (mk.y & 0x7fff0000u) ? __uint_as_float(r[q * 4 + 3]) + bi.w : 0.f;
+              const uint32_t* rr = half ? r1 : r0;
+              float v0 = __uint_as_float(rr[q * 4 + 0]) + bi.x, v1 = __uint_as_float(rr[q * 4 + 1]) + bi.y;
+              float v2 = __uint_as_float(rr[q * 4 + 2]) + bi.z, v3 = __uint_as_float(rr[q * 4 + 3]) + bi.w;
+              if (p.maskplane) {     // word j of mk holds columns 2j, 2j+1 of this 64-column step: non-zero bf16 <=> activation > 0
+                const uint32_t ma = mk[half * 16 + q * 2], mb = mk[half * 16 + q * 2 + 1];
+                v0 = (ma & 0x00007fffu) ? v0 : 0.f; v1 = (ma & 0x7fff0000u) ? v1 : 0.f;
+                v2 = (mb & 0x00007fffu) ? v2 : 0.f; v3 = (mb & 0x7fff0000u) ? v3 : 0.f;
               } else {
-                v0 = fmaxf(__uint_as_float(r[q * 4 + 0]) + bi.x, 0.f); v1 = fmaxf(__uint_as_float(r[q * 4 + 1]) + bi.y, 0.f);
-                v2 = fmaxf(__uint_as_float(r[q * 4 + 2]) + bi.z, 0.f); v3 = fmaxf(__uint_as_float(r[q * 4 + 3]) + bi.w, 0.f);
+                v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); v2 = fmaxf(v2, 0.f); v3 = fmaxf(v3, 0.f);
               }
-              split_bf16(v0, hi[q * 4 + 0], lo[q * 4 + 0]); split_bf16(v1, hi[q * 4 + 1], lo[q * 4 + 1]);
-              split_bf16(v2, hi[q * 4 + 2], lo[q * 4 + 2]); split_bf16(v3, hi[q * 4 + 3], lo[q * 4 + 3]);
-            }
-            uint4* oh = reinterpret_cast<uint4*>(p.out_hi + m * p.N + c0);
-            const uint4* sh = reinterpret_cast<const uint4*>(hi);
-            oh[0] = sh[0]; oh[1] = sh[1]; oh[2] = sh[2]; oh[3] = sh[3];
-            if (p.planes == 2) {
-              uint4* ol = reinterpret_cast<uint4*>(p.out_lo + m * p.N + c0);
-              const uint4* sl = reinterpret_cast<const uint4*>(lo);
-              ol[0] = sl[0]; ol[1] = sl[1]; ol[2] = sl[2]; ol[3] = sl[3];
+              split2_bf16(v0, v1, hw[half * 16 + q * 2], lw[half * 16 + q * 2]);
+              split2_bf16(v2, v3, hw[half * 16 + q * 2 + 1], lw[half * 16 + q * 2 + 1]);
             }
           }
+          warp_store_rows64_ld(stage, hw, p.out_hi, m_warp, c0, p.M, lane, p.N);
+          if (p.planes == 2) warp_store_rows64_ld(stage, lw, p.out_lo, m_warp, c0, p.M, lane, p.N);
         }
       } else {   // LayerNorm over the 128 columns of this row, then edge mask
         float v[128];
@@ -1356,7 +1435,7 @@ tc_embed_fused_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_cons
   }
 }
 
-constexpr size_t TC_SMEM_BYTES = 1024 + (size_t)(TC_SA + TC_SB) * 2 * TC_PLANE_BYTES + 256 + 4096;
+constexpr size_t TC_SMEM_BYTES = 1024 + (size_t)(TC_SA + TC_SB) * 2 * TC_PLANE_BYTES + 1024 + 4 * 4096;   // rings | barriers (1 KB) | 4 x 4 KB epilogue staging tiles
 
 // fp32 [M, ld] (first K columns) -> dense bf16 hi/lo planes [M, K]  (A operand of a node-path tensor-core linear)
 __global__ void split_planes_kernel(const float* __restrict__ x, int ld, long long M, int K, __nv_bfloat16* __restrict__ hi,
