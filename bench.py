@@ -262,15 +262,15 @@ def run_train(args):
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
-    l0 = eng.lib.fd_num_params()   # noqa (keeps the lib symbol table warm)
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
     dev_ms = e2e_ms = 0.0
     exposed = 0.0
-    launches0 = None
+    launches = 0
     losses = []
     for i in range(args.steps):          # the two legs interleaved step by step (same clock / power state)
+        l0 = eng.launch_count()
         barrier(); ev[0].record(); dev_step(); ev[1].record(); barrier()
-        dev_ms += ev[0].elapsed_time(ev[1]); exposed += ts.exposed_comm_ms()
+        dev_ms += ev[0].elapsed_time(ev[1]); exposed += ts.exposed_comm_ms(); launches += eng.launch_count() - l0
         barrier(); t0 = time.perf_counter(); losses.append(e2e_step()); barrier()
         e2e_ms += (time.perf_counter() - t0) * 1e3
     t = torch.tensor([dev_ms, e2e_ms, exposed], device=dev, dtype=torch.float64)
@@ -293,7 +293,7 @@ def run_train(args):
                            "l2": "not flushed: every layer streams the %.0f MB fp32 edge tensor (> 126 MB L2)" % (B * N * N * 128 * 4 / 1e6)},
                 "e2e": {"value": world * B / e2e_s, "unit": "examples/s", "ms_per_step": e2e_s * 1e3, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8},
                 "comm_exposed_ms_per_step": exposed_ms, "allreduce_bytes_per_step": int(ts.grads.numel() * 4) if world > 1 else 0,
-                "final_loss": losses[-1] if losses else None, "clocks": clk,
+                "final_loss": losses[-1] if losses else None, "clocks": clk, "gpu_launches": int(launches),
                 "roofline": {"bound": "tensor", "kernel": "whole training step (forward + dgrad + wgrad GEMMs: %s)" % {"fp32": "fp32 CUDA cores", "bf16x3": "mm3_kernel, mma.sync split-bf16", "tc": "edge-tensor forward/dgrad on tc_gemm_kernel (tcgen05), weight gradients and node path on mm3_kernel (mma.sync); split-bf16"}[args.train_gemm],
                              "achieved": ach, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": ach / pk["bf16_tflops_sustained"],
                              "peak_source": pk["source"], "traffic": None, "executed_flops_per_step": fl},

@@ -215,6 +215,9 @@ int fd_sample_dev(fd_handle h, const fd_sample_cfg* cfg, const float* rigids_ini
 int fd_num_stages(void);
 const char* fd_stage_name(int i);
 int fd_set_stage_timing(fd_handle h, int on);
+/* Kernels this handle has launched so far (training and forward calls add to it; fd_sample* restart it at 0): take the difference around a
+ * region to count its launches — bench.py's `gpu_launches` of the training step. */
+int64_t fd_launch_count(fd_handle h);
 int fd_stage_times(fd_handle h, double* ms_out /* [fd_num_stages()] */, int64_t* launches_out);
 int64_t fd_forward_flops(int B, int N, int executed);   /* algorithmic FLOPs of one forward */
 

@@ -89,6 +89,7 @@ SYMBOLS = {
     "fd_num_stages": (C.c_int, []),
     "fd_stage_name": (C.c_char_p, [C.c_int]),
     "fd_set_stage_timing": (C.c_int, [c_voidp, C.c_int]),
+    "fd_launch_count": (C.c_int64, [c_voidp]),
     "fd_stage_times": (C.c_int, [c_voidp, c_f64p, C.POINTER(C.c_int64)]),
     "fd_forward_flops": (C.c_int64, [C.c_int, C.c_int, C.c_int]),
     "fd_debug_tc_profile": (C.c_int, [c_voidp, C.c_int, C.POINTER(C.c_longlong)]),

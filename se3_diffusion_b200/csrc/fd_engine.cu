@@ -1483,6 +1483,7 @@ extern "C" int fd_loss_backward(fd_handle h, int B, int N, const fd_loss_in* in,
     CK(cudaGetLastError());
     loss_bwd2_kernel<<<grid, 256, smem2, st>>>(a, h->d_loss_acc);
     CK(cudaGetLastError());
+    h->launches += 2;
   }
   return FD_OK;
 }
@@ -1494,6 +1495,7 @@ extern "C" int fd_adam_step(fd_handle h, float* params, const float* grads, floa
   adam_kernel<<<(unsigned)((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(params, grads, exp_avg, exp_avg_sq, n, (float)lr, (float)beta1,
                                                                                           (float)beta2, (float)eps, (float)bc1, (float)bc2, (float)grad_scale);
   CK(cudaGetLastError());
+  h->launches++;
   return FD_OK;
 }
 
@@ -1511,6 +1513,7 @@ extern "C" int fd_debug_tc_profile(fd_handle h, int on, long long* out32) {
   return FD_OK;
 }
 
+extern "C" int64_t fd_launch_count(fd_handle h) { return h ? (int64_t)h->launches : -1; }
 extern "C" int fd_num_stages(void) { return ST_COUNT; }
 extern "C" const char* fd_stage_name(int i) { return (i < 0 || i >= ST_COUNT) ? nullptr : kStageNames[i]; }
 extern "C" int fd_set_stage_timing(fd_handle h, int on) {
@@ -1572,6 +1575,7 @@ extern "C" int fd_loss_forward(fd_handle h, int B, int N, const fd_loss_in* in, 
     CK(cudaGetLastError());
     loss_finalize_kernel<<<(B + 127) / 128, 128, 0, st>>>(a, h->d_loss_acc, B);
     CK(cudaGetLastError());
+    h->launches += 2;
   }
   return FD_OK;
 }

@@ -278,6 +278,10 @@ class FrameDiffEngine:
     def stage_timing(self, on: bool):
         check(self.lib.fd_set_stage_timing(self._h, int(on)))
 
+    def launch_count(self) -> int:
+        """Kernels launched by this handle so far (difference it around a region; `sample*` restart it)."""
+        return int(self.lib.fd_launch_count(self._h))
+
     def stage_times(self):
         n = self.lib.fd_num_stages()
         ms = (C.c_double * n)()
