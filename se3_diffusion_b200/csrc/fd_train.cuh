@@ -64,7 +64,8 @@ inline cudaError_t launch_colsum_narrow(const float* X, long long M, int N, floa
   return cudaGetLastError();
 }
 inline cudaError_t launch_colsum(const float* X, int ld, long long M, int N, float* out, cudaStream_t st) {
-  int slabs = (int)min((long long)1024, max((long long)1, M / 256));
+  // >= 32 rows per thread; a node-level tensor (a few thousand rows) still spreads over tens of CTAs instead of eight
+  int slabs = (int)min((long long)1024, max((long long)1, M / 32));
   colsum_kernel<<<dim3((N + 127) / 128, slabs), 128, 0, st>>>(X, ld, M, N, out);
   return cudaGetLastError();
 }

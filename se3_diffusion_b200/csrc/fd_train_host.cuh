@@ -172,6 +172,21 @@ struct TG {
     GemmArgs a;
     a.A = dy; a.lda = lddy; a.B = W; a.ldb = ldw; a.C = dx; a.ldc = lddx; a.M = (int)M; a.N = Kin; a.K = Nout; a.accumulate = accumulate;
     a.relumask = relumask; a.ldm = ldm;
+    // node-level data gradients with a long reduction (d IPA projections, d linear_out: a few thousand rows, K >= 512) fill a fifth of the
+    // SMs with 128x128 tiles: split K over the idle ones and combine the partial tiles with the atomic epilogue
+    const long long tiles = ((M + 127) / 128) * ((Kin + 127) / 128);
+    if (h->train_gemm >= 1 && !relumask && Nout >= 512 && tiles * 2 <= h->sm_count && !err) {
+      int sp = (int)(h->sm_count / tiles);
+      if (sp > Nout / 256) sp = Nout / 256;
+      if (sp > 1) {
+        if (!accumulate) {
+          if (cudaMemset2DAsync(dx, (size_t)lddx * sizeof(float), 0, (size_t)Kin * sizeof(float), (size_t)M, st) != cudaSuccess) {
+            err = fail(FD_ECUDA, "dgrad: clearing the split-K output failed"); return;
+          }
+        }
+        a.accumulate = false; a.atomic = 1; a.splits = sp;
+      }
+    }
     gemm(a, false);
   }
   // dW[Nout][lddw] += dy[rows,Nout]^T x[rows,Kin]   (atomic accumulation, split over the rows)
