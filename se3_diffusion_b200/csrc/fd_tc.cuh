@@ -215,7 +215,7 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
 constexpr int TC_BM = 128, TC_BK = 64, TC_NC = 128;           // tile rows, k per stage, n-chunk
 constexpr int TC_PLANE_BYTES = TC_BM * TC_BK * 2;             // 16 KB: one bf16 plane of a 128×64 tile
 constexpr int TC_SA = 2, TC_SB = 4;                           // ring depths
-constexpr int TC_THREADS = 192;
+constexpr int TC_THREADS = 192;                                // warp 0 TMA, warp 1 MMA, warps 2..5 epilogue (EG = 2: warps 2..9)
 constexpr int TC_TMEM_COLS = 512;
 
 enum { TC_EPI_RELU = 0, TC_EPI_LN = 1, TC_EPI_F32 = 2 };
@@ -259,6 +259,11 @@ struct TcGemmParams {
                                       // 128-wide tile, UMMA descriptors with LBO = 8 KB (next 64-column block) and SBO = 1 KB (next 8 K rows)
   int atomic;                         // out_f32[m][n] += alpha*acc through atomicAdd (weight gradients: the k-slices of one output tile are
                                       // the batched mode's inner batches with o_s1 = 0); bias / relu / mask / residual are ignored
+  int eg;                             // 2: ten-warp variant (two epilogue groups) — pays on edge-sized GEMMs with wide outputs
+  int sa;                             // stages of the activation ring (0 = 2; the weight ring takes 6 - sa)
+  int chunk_minor;                    // > 0: work item lt -> (row tile lt / chunk_minor, n-group lt % chunk_minor): the n-groups of one row tile run
+                                      // on neighbouring CTAs at the same time, so the A tile comes from DRAM once and from L2 afterwards
+                                      // (0: lt -> (lt % m_tiles, lt / m_tiles))
 };
 
 __device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&r)[32]);
@@ -324,7 +329,32 @@ __device__ __forceinline__ void warp_load_rows64_ld(uint32_t stage, uint32_t (&w
   __syncwarp();
 }
 
-__global__ void __launch_bounds__(TC_THREADS, 1)
+// Row gather for the node terms of edge rows: thread `lane` wants 32 fp32 (128 B) starting at its own pointer `mine` (null = zeros).  Read
+// row-per-thread, one instruction touches 32 different lines 16 bytes at a time (every access an L2 round trip, the table rows are 4 KB apart);
+// here eight lanes fetch one row's 128 bytes, four rows per instruction, and the tile is transposed through the warp's staging buffer.
+__device__ __forceinline__ void warp_gather_rows32f(uint32_t stage, uint32_t (&w)[32], const float* mine, int lane) {
+  const unsigned long long pm = reinterpret_cast<unsigned long long>(mine);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int r = k * 4 + (lane >> 3), u = lane & 7;
+    const unsigned long long pr = __shfl_sync(0xffffffffu, pm, r);
+    uint4 val = make_uint4(0u, 0u, 0u, 0u);
+    if (pr) val = *reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(pr) + u * 4);
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage + (uint32_t)(r * 128 + ((u ^ (r & 7)) << 4))), "r"(val.x), "r"(val.y),
+                 "r"(val.z), "r"(val.w)
+                 : "memory");
+  }
+  __syncwarp();
+#pragma unroll
+  for (int u = 0; u < 8; ++u)
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w[4 * u]), "=r"(w[4 * u + 1]), "=r"(w[4 * u + 2]), "=r"(w[4 * u + 3])
+                 : "r"(stage + (uint32_t)(lane * 128 + ((u ^ (lane & 7)) << 4))) : "memory");
+  __syncwarp();
+}
+
+// EG = epilogue groups: 1 -> 192 threads (up to 255 registers), 2 -> 320 threads (ten warps: three on one scheduler, so 168 registers)
+template <int EG>
+__global__ void __launch_bounds__(64 + 128 * EG, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap mA0h, const __grid_constant__ CUtensorMap mA0l,
                const __grid_constant__ CUtensorMap mA1h, const __grid_constant__ CUtensorMap mA1l,
                const __grid_constant__ CUtensorMap mBh, const __grid_constant__ CUtensorMap mBl, const TcGemmParams p) {
@@ -332,17 +362,22 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mA0h, const __grid_constant__
   // carve: A ring | B ring | barriers
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t a_ring = base;
-  const uint32_t b_ring = a_ring + TC_SA * 2 * TC_PLANE_BYTES;
-  const uint32_t bar0 = b_ring + TC_SB * 2 * TC_PLANE_BYTES;
-  // barrier slots (8 B each): a_full[SA], a_empty[SA], b_full[SB], b_empty[SB], tmem_full, tmem_empty, tmem_ptr
-  auto a_full = [&](int s) { return bar0 + 8u * s; };
-  auto a_empty = [&](int s) { return bar0 + 8u * (TC_SA + s); };
-  auto b_full = [&](int s) { return bar0 + 8u * (2 * TC_SA + s); };
-  auto b_empty = [&](int s) { return bar0 + 8u * (2 * TC_SA + TC_SB + s); };
+  // the six 32 KB stages are split between the two rings per launch: SA for the activation operand, the rest for the weights.  A GEMM whose A
+  // streams from DRAM (edge-sized M) is bound by (A stages in flight) / (DRAM latency): it takes four; the node-path GEMMs, whose A sits in L2 and
+  // which need up to three weight chunks per A block, keep 2 + 4
+  constexpr uint32_t TC_S = TC_SA + TC_SB;
+  const uint32_t SA = p.sa > 0 ? (uint32_t)p.sa : (uint32_t)TC_SA, SB = TC_S - SA;
+  const uint32_t b_ring = a_ring + SA * 2 * TC_PLANE_BYTES;
+  const uint32_t bar0 = a_ring + TC_S * 2 * TC_PLANE_BYTES;
+  // barrier slots (8 B each): a_full[6], a_empty[6], b_full[6], b_empty[6], tmem_full[2], tmem_empty[2], tmem_ptr
+  auto a_full = [&](uint32_t s) { return bar0 + 8u * s; };
+  auto a_empty = [&](uint32_t s) { return bar0 + 8u * (TC_S + s); };
+  auto b_full = [&](uint32_t s) { return bar0 + 8u * (2 * TC_S + s); };
+  auto b_empty = [&](uint32_t s) { return bar0 + 8u * (3 * TC_S + s); };
   // accumulators are double-buffered in tensor memory (two 256-column halves) whenever a work item needs <= 256 columns
-  auto tmem_full = [&](uint32_t x) { return bar0 + 8u * (2 * TC_SA + 2 * TC_SB + x); };
-  auto tmem_empty = [&](uint32_t x) { return bar0 + 8u * (2 * TC_SA + 2 * TC_SB + 2 + x); };
-  const uint32_t tmem_ptr_addr = bar0 + 8u * (2 * TC_SA + 2 * TC_SB + 4);
+  auto tmem_full = [&](uint32_t x) { return bar0 + 8u * (4 * TC_S + x); };
+  auto tmem_empty = [&](uint32_t x) { return bar0 + 8u * (4 * TC_S + 2 + x); };
+  const uint32_t tmem_ptr_addr = bar0 + 8u * (4 * TC_S + 4);
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int KB = p.KB0 + p.KB1;
@@ -351,9 +386,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mA0h, const __grid_constant__
   const uint32_t stage_bytes = (uint32_t)p.planes * TC_PLANE_BYTES;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < TC_SA; ++s) { mbar_init(a_full(s), 1); mbar_init(a_empty(s), 1); }
-    for (int s = 0; s < TC_SB; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
-    for (uint32_t x = 0; x < 2; ++x) { mbar_init(tmem_full(x), 1); mbar_init(tmem_empty(x), 4); }   // empty: one arrive per epilogue warp
+    for (uint32_t s = 0; s < SA; ++s) { mbar_init(a_full(s), 1); mbar_init(a_empty(s), 1); }
+    for (uint32_t s = 0; s < SB; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
+    for (uint32_t x = 0; x < 2; ++x) { mbar_init(tmem_full(x), 1); mbar_init(tmem_empty(x), 4 * EG); }   // empty: one arrive per epilogue warp
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     tma_prefetch_desc(&mA0h); tma_prefetch_desc(&mBh);
     if (p.planes == 2) { tma_prefetch_desc(&mA0l); tma_prefetch_desc(&mBl); }
@@ -372,7 +407,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mA0h, const __grid_constant__
   if (warp == 0) {
     // ================================ TMA producer ================================
     {
-      uint32_t ia = 0, ib = 0;   // running stage counters (whole warp runs the loop; one elected lane issues)
+      uint32_t sa = 0, pa = 0, sb = 0, pb = 0;   // ring positions and phase bits (whole warp runs the loop; one elected lane issues)
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         int lt = tile, a_r = 0, a_k = 0, b_r = 0, b_k = 0;
         if (p.bat_inner) {
@@ -381,9 +416,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mA0h, const __grid_constant__
           a_r = bo * p.a_row_s0 + bi * p.a_row_s1; a_k = bi * p.a_k_s1;
           b_r = bo * p.b_row_s0 + bi * p.b_row_s1; b_k = p.b_k0 + bi * p.b_k_s1;
         }
-        const int m0 = (lt % p.m_tiles) * TC_BM + a_r, n0 = (lt / p.m_tiles) * NCH * TC_NC + b_r;
+        const int mt = p.chunk_minor ? lt / p.chunk_minor : lt % p.m_tiles, ng = p.chunk_minor ? lt - mt * p.chunk_minor : lt / p.m_tiles;
+        const int m0 = mt * TC_BM + a_r, n0 = ng * NCH * TC_NC + b_r;
         for (int kb = 0; kb < KB; ++kb) {
-          const uint32_t sa = ia % TC_SA, pa = (ia / TC_SA) & 1u;
           mbar_wait(a_empty(sa), pa ^ 1u);
           const bool first = kb < p.KB0;
           const int ka = (first ? kb : kb - p.KB0) * TC_BK + a_k;
@@ -399,9 +434,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mA0h, const __grid_constant__
             }
           }
           __syncwarp();
-          ++ia;
+          if (++sa == SA) { sa = 0; pa ^= 1u; }
           for (int c = 0; c < NCH; ++c) {
-            const uint32_t sb = ib % TC_SB, pb = (ib / TC_SB) & 1u;
             mbar_wait(b_empty(sb), pb ^ 1u);
             const uint32_t dstB = b_ring + sb * 2 * TC_PLANE_BYTES;
             if (elect_one()) {
@@ -416,7 +450,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mA0h, const __grid_constant__
               }
             }
             __syncwarp();
-            ++ib;
+            if (++sb == SB) { sb = 0; pb ^= 1u; }
           }
         }
       }
@@ -425,18 +459,16 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mA0h, const __grid_constant__
     // ================================ MMA issuer ================================
     {
       const uint32_t idesc = make_idesc_bf16(TC_BM, p.mma_n) | (p.mn_major ? ((1u << 15) | (1u << 16)) : 0u);      // a_major / b_major = MN
-      uint32_t ia = 0, ib = 0, it = 0;
+      uint32_t sa = 0, pa = 0, sb = 0, pb = 0, it = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
         const uint32_t buf = dbuf ? (it & 1u) : 0u, use = dbuf ? (it >> 1) : it;
         mbar_wait(tmem_empty(buf), (use & 1u) ^ 1u);      // epilogue has drained this half's previous accumulators
         tc_fence_after();
         for (int kb = 0; kb < KB; ++kb) {
-          const uint32_t sa = ia % TC_SA, pa = (ia / TC_SA) & 1u;
           mbar_wait(a_full(sa), pa);
           tc_fence_after();
           const uint32_t aH = a_ring + sa * 2 * TC_PLANE_BYTES, aL = aH + TC_PLANE_BYTES;
           for (int c = 0; c < NCH; ++c) {
-            const uint32_t sb = ib % TC_SB, pb = (ib / TC_SB) & 1u;
             mbar_wait(b_full(sb), pb);
             tc_fence_after();
             const uint32_t bH = b_ring + sb * 2 * TC_PLANE_BYTES, bL = bH + TC_PLANE_BYTES;
@@ -454,17 +486,20 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mA0h, const __grid_constant__
               tc_commit(b_empty(sb));     // frees this weight stage once the MMAs above retire
             }
             __syncwarp();
-            ++ib;
+            if (++sb == SB) { sb = 0; pb ^= 1u; }
           }
           tc_commit_elect(a_empty(sa));
-          ++ia;
+          if (++sa == SA) { sa = 0; pa ^= 1u; }
         }
         tc_commit_elect(tmem_full(buf));      // accumulators complete -> epilogue
       }
     }
   } else {
-    // ================================ epilogue (warps 2..5) ================================
+    // ================================ epilogue (warps 2..9) ================================
+    // two groups of four warps (one warp per TMEM lane quadrant in each): the groups take alternate column steps of every work item, so each
+    // scheduler has two epilogue warps to interleave (one warp alone is bound by its own instruction latencies)
     const int quad = warp & 3;                       // TMEM lane quadrant this warp may access
+    const int grp = EG == 2 ? (warp - 2) >> 2 : 0;
     const int row_in_tile = quad * 32 + lane;
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
@@ -477,8 +512,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mA0h, const __grid_constant__
         lt = tile - bat * p.bat_tiles;
         o_off = bo * p.o_s0 + bi * p.o_s1;
       }
-      const long long m = (long long)(lt % p.m_tiles) * TC_BM + row_in_tile;
-      const int n0 = (lt / p.m_tiles) * NCH * TC_NC;
+      const int mt = p.chunk_minor ? lt / p.chunk_minor : lt % p.m_tiles, ng = p.chunk_minor ? lt - mt * p.chunk_minor : lt / p.m_tiles;
+      const long long m = (long long)mt * TC_BM + row_in_tile;
+      const int n0 = ng * NCH * TC_NC;
       const bool valid = m < p.M;
       const float* add_i = nullptr; const float* add_j = nullptr;
       float emask = 1.f;
@@ -497,13 +533,16 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mA0h, const __grid_constant__
       if (p.epi == TC_EPI_F32) {
         const float rm = (valid && p.rowmask) ? p.rowmask[m] : 1.f;
         const int ncols = min(NCH * TC_NC, ((p.n_valid - n0 + 31) / 32) * 32);     // skip accumulator columns beyond the valid width
-        for (int c0 = 0; c0 < ncols; c0 += 32) {
+        for (int c0 = grp * 32; c0 < ncols; c0 += 32 * EG) {
           const int n = n0 + c0;
           const bool act = valid && n < p.n_valid;
           // bias / residual of this 32-column group are requested before the accumulator read: their latencies overlap instead of
           // serialising behind the stores (the compiler cannot hoist them itself: out_f32 may alias)
           float4 bv[8], rv[8];
           const float* rrow = (act && p.residual) ? p.residual + m * p.ldr + n : nullptr;
+          const bool gather_j = p.rowadd != nullptr && n + 32 <= p.n_valid;       // warp-uniform: the j-side node terms come through the staging tile
+          uint32_t aj[32];
+          if (gather_j) warp_gather_rows32f(bar0 + 1024u + (uint32_t)(warp - 2) * 4096u, aj, add_j ? add_j + n : nullptr, lane);
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
             const bool in = act && n + q * 4 < p.n_valid;     // n_valid is a multiple of 4 for every linear routed here
@@ -511,7 +550,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mA0h, const __grid_constant__
             rv[q] = (in && rrow) ? *reinterpret_cast<const float4*>(rrow + q * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
             if (in && add_i) {
               const float4 x = *reinterpret_cast<const float4*>(add_i + n + q * 4);
-              const float4 y = *reinterpret_cast<const float4*>(add_j + n + q * 4);
+              float4 y;
+              if (gather_j) y = make_float4(__uint_as_float(aj[q * 4]), __uint_as_float(aj[q * 4 + 1]), __uint_as_float(aj[q * 4 + 2]), __uint_as_float(aj[q * 4 + 3]));
+              else y = *reinterpret_cast<const float4*>(add_j + n + q * 4);
               bv[q].x += x.x + y.x; bv[q].y += x.y + y.y; bv[q].z += x.z + y.z; bv[q].w += x.w + y.w;
             }
           }
@@ -560,43 +601,66 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mA0h, const __grid_constant__
         // 64 columns per step: accumulator -> (+bias, +node terms) -> ReLU or ReLU-mask -> bf16 hi/lo -> coalesced stores through the warp's staging tile
         const uint32_t stage = bar0 + 1024u + (uint32_t)(warp - 2) * 4096u;
         const long long m_warp = m - lane;
-        for (int c0 = 0; c0 < p.N; c0 += 64) {
-          uint32_t r0[32], r1[32];
-          tmem_ld32_nowait(trow + (uint32_t)c0, r0);
-          tmem_ld32_nowait(trow + (uint32_t)(c0 + 32), r1);
-          uint32_t mk[32];
-          if (p.maskplane) warp_load_rows64_ld(stage, mk, p.maskplane, m_warp, c0, p.M, lane, p.N);
-          tmem_ld_wait();
-          uint32_t hw[32], lw[32];
+        if (p.maskplane) {
+          // backward of a ReLU: acc (+bias) where the activation plane is non-zero, 0 elsewhere
+          for (int c0 = grp * 64; c0 < NCH * TC_NC; c0 += 64 * EG) {      // accumulator column c0 = output column n0 + c0
+            uint32_t r0[32], r1[32];
+            tmem_ld32_nowait(trow + (uint32_t)c0, r0);
+            tmem_ld32_nowait(trow + (uint32_t)(c0 + 32), r1);
+            uint32_t mk[32];
+            warp_load_rows64_ld(stage, mk, p.maskplane, m_warp, n0 + c0, p.M, lane, p.N);
+            tmem_ld_wait();
+            uint32_t hw[32], lw[32];
 #pragma unroll
-          for (int half = 0; half < 2; ++half) {
+            for (int half = 0; half < 2; ++half) {
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              const int cc = c0 + half * 32 + q * 4;
-              float4 bi = (valid && p.bias) ? *reinterpret_cast<const float4*>(p.bias + cc) : make_float4(0.f, 0.f, 0.f, 0.f);
-              if (add_i) {
-                const float4 x = *reinterpret_cast<const float4*>(add_i + cc);
-                const float4 y = *reinterpret_cast<const float4*>(add_j + cc);
-                bi.x += x.x + y.x; bi.y += x.y + y.y; bi.z += x.z + y.z; bi.w += x.w + y.w;
-              }
-              const uint32_t* rr = half ? r1 : r0;
-              float v0 = __uint_as_float(rr[q * 4 + 0]) + bi.x, v1 = __uint_as_float(rr[q * 4 + 1]) + bi.y;
-              float v2 = __uint_as_float(rr[q * 4 + 2]) + bi.z, v3 = __uint_as_float(rr[q * 4 + 3]) + bi.w;
-              if (p.maskplane) {     // word j of mk holds columns 2j, 2j+1 of this 64-column step: non-zero bf16 <=> activation > 0
+              for (int q = 0; q < 8; ++q) {
+                const int cc = n0 + c0 + half * 32 + q * 4;
+                const float4 bi = (valid && p.bias) ? *reinterpret_cast<const float4*>(p.bias + cc) : make_float4(0.f, 0.f, 0.f, 0.f);
+                const uint32_t* rr = half ? r1 : r0;
+                float v0 = __uint_as_float(rr[q * 4 + 0]) + bi.x, v1 = __uint_as_float(rr[q * 4 + 1]) + bi.y;
+                float v2 = __uint_as_float(rr[q * 4 + 2]) + bi.z, v3 = __uint_as_float(rr[q * 4 + 3]) + bi.w;
+                // word j of mk holds columns 2j, 2j+1 of this 64-column step: non-zero bf16 <=> activation > 0
                 const uint32_t ma = mk[half * 16 + q * 2], mb = mk[half * 16 + q * 2 + 1];
                 v0 = (ma & 0x00007fffu) ? v0 : 0.f; v1 = (ma & 0x7fff0000u) ? v1 : 0.f;
                 v2 = (mb & 0x00007fffu) ? v2 : 0.f; v3 = (mb & 0x7fff0000u) ? v3 : 0.f;
-              } else {
-                v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); v2 = fmaxf(v2, 0.f); v3 = fmaxf(v3, 0.f);
+                split2_bf16(v0, v1, hw[half * 16 + q * 2], lw[half * 16 + q * 2]);
+                split2_bf16(v2, v3, hw[half * 16 + q * 2 + 1], lw[half * 16 + q * 2 + 1]);
               }
-              split2_bf16(v0, v1, hw[half * 16 + q * 2], lw[half * 16 + q * 2]);
-              split2_bf16(v2, v3, hw[half * 16 + q * 2 + 1], lw[half * 16 + q * 2 + 1]);
             }
+            warp_store_rows64_ld(stage, hw, p.out_hi, m_warp, n0 + c0, p.M, lane, p.N);
+            if (p.planes == 2) warp_store_rows64_ld(stage, lw, p.out_lo, m_warp, n0 + c0, p.M, lane, p.N);
           }
-          warp_store_rows64_ld(stage, hw, p.out_hi, m_warp, c0, p.M, lane, p.N);
-          if (p.planes == 2) warp_store_rows64_ld(stage, lw, p.out_lo, m_warp, c0, p.M, lane, p.N);
+        } else {
+          // forward: relu(acc + bias + node terms); the j-side node terms of the warp's 32 rows are gathered through the staging tile
+          for (int c0 = grp * 64; c0 < NCH * TC_NC; c0 += 64 * EG) {
+            uint32_t hw[32], lw[32];
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+              uint32_t r[32], aj[32];
+              tmem_ld32_nowait(trow + (uint32_t)(c0 + half * 32), r);
+              if (p.rowadd) warp_gather_rows32f(stage, aj, add_j ? add_j + n0 + c0 + half * 32 : nullptr, lane);
+              tmem_ld_wait();
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {
+                const int cc = n0 + c0 + half * 32 + q * 4;
+                float4 bi = (valid && p.bias) ? *reinterpret_cast<const float4*>(p.bias + cc) : make_float4(0.f, 0.f, 0.f, 0.f);
+                if (add_i) {
+                  const float4 x = *reinterpret_cast<const float4*>(add_i + cc);
+                  bi.x += x.x + __uint_as_float(aj[q * 4]); bi.y += x.y + __uint_as_float(aj[q * 4 + 1]);
+                  bi.z += x.z + __uint_as_float(aj[q * 4 + 2]); bi.w += x.w + __uint_as_float(aj[q * 4 + 3]);
+                }
+                const float v0 = fmaxf(__uint_as_float(r[q * 4 + 0]) + bi.x, 0.f), v1 = fmaxf(__uint_as_float(r[q * 4 + 1]) + bi.y, 0.f);
+                const float v2 = fmaxf(__uint_as_float(r[q * 4 + 2]) + bi.z, 0.f), v3 = fmaxf(__uint_as_float(r[q * 4 + 3]) + bi.w, 0.f);
+                split2_bf16(v0, v1, hw[half * 16 + q * 2], lw[half * 16 + q * 2]);
+                split2_bf16(v2, v3, hw[half * 16 + q * 2 + 1], lw[half * 16 + q * 2 + 1]);
+              }
+            }
+            warp_store_rows64_ld(stage, hw, p.out_hi, m_warp, n0 + c0, p.M, lane, p.N);
+            if (p.planes == 2) warp_store_rows64_ld(stage, lw, p.out_lo, m_warp, n0 + c0, p.M, lane, p.N);
+          }
         }
-      } else {   // LayerNorm over the 128 columns of this row, then edge mask
+      } else if (grp == 0) {   // LayerNorm over the 128 columns of this row, then edge mask (whole rows per thread: one group works)
         float v[128];
 #pragma unroll
         for (int c0 = 0; c0 < 128; c0 += 32) {
@@ -1435,7 +1499,7 @@ tc_embed_fused_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_cons
   }
 }
 
-constexpr size_t TC_SMEM_BYTES = 1024 + (size_t)(TC_SA + TC_SB) * 2 * TC_PLANE_BYTES + 1024 + 4 * 4096;   // rings | barriers (1 KB) | 4 x 4 KB epilogue staging tiles
+constexpr size_t TC_SMEM_BYTES = 1024 + (size_t)(TC_SA + TC_SB) * 2 * TC_PLANE_BYTES + 1024 + 8 * 4096;   // rings | barriers (1 KB) | 8 x 4 KB epilogue staging tiles
 
 // fp32 [M, ld] (first K columns) -> dense bf16 hi/lo planes [M, K]  (A operand of a node-path tensor-core linear)
 __global__ void split_planes_kernel(const float* __restrict__ x, int ld, long long M, int K, __nv_bfloat16* __restrict__ hi,
@@ -1610,6 +1674,7 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 static PFN_encodeTiled g_encode = nullptr;
 static int g_tc_sms = 148;
+static int g_tc_eg = 0;             // epilogue groups of tc_gemm_kernel: 0 = per launch (TcGemmParams::eg); FD_TC_EG=1|2 forces one variant (A/B runs)
 
 static long long* g_tc_prof = nullptr;   // device [32]; set by fd_debug_tc_profile
 // ------------------------------------------------------------------------------------------------------------------
@@ -1978,7 +2043,9 @@ inline int tc_init(int sm_count) {
   cudaDriverEntryPointQueryResult q;
   if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn) return -2;
   g_encode = (PFN_encodeTiled)fn;
-  if (cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES) != cudaSuccess) return -2;
+  if (cudaFuncSetAttribute(tc_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES) != cudaSuccess) return -2;
+  if (cudaFuncSetAttribute(tc_gemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES) != cudaSuccess) return -2;
+  if (const char* e = getenv("FD_TC_EG")) g_tc_eg = atoi(e) == 2 ? 2 : (atoi(e) == 1 ? 1 : 0);
   if (cudaFuncSetAttribute(tc_edge_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FU_SMEM_BYTES) != cudaSuccess) return -2;
   if (cudaFuncSetAttribute(tc_edge_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FU_SMEM_BYTES) != cudaSuccess) return -2;
   g_tc_cluster = getenv("FD_TC_CLUSTER") ? atoi(getenv("FD_TC_CLUSTER")) : g_tc_cluster;
@@ -2169,12 +2236,15 @@ inline int tc_bind_workspace(TcWorkspace& w, char* p, int B, int N) {
 
 inline int tc_launch_maps(const CUtensorMap& a0h, const CUtensorMap& a0l, const CUtensorMap& a1h, const CUtensorMap& a1l, const CUtensorMap& bh,
                           const CUtensorMap& bl, TcGemmParams p, cudaStream_t st, long long* launches) {
-  if (p.epi != TC_EPI_F32) {
+  if (p.epi == TC_EPI_RELU) {          // one 128-column chunk per work item (double-buffered accumulators), chunks of a row tile adjacent
+    p.m_tiles = (p.M + TC_BM - 1) / TC_BM; p.nch = 1; p.chunk_minor = p.N / TC_NC; p.num_tiles = p.m_tiles * p.chunk_minor; p.n_valid = p.N;
+  } else if (p.epi != TC_EPI_F32) {
     p.m_tiles = (p.M + TC_BM - 1) / TC_BM; p.nch = p.N / TC_NC; p.num_tiles = p.m_tiles; p.n_valid = p.N;
   }
   if (p.mma_n == 0) p.mma_n = TC_NC;
   const int grid = p.num_tiles < g_tc_sms ? p.num_tiles : g_tc_sms;
-  tc_gemm_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(a0h, a0l, a1h, a1l, bh, bl, p);
+  if (g_tc_eg == 2 || (g_tc_eg == 0 && p.eg == 2)) tc_gemm_kernel<2><<<grid, 320, TC_SMEM_BYTES, st>>>(a0h, a0l, a1h, a1l, bh, bl, p);
+  else tc_gemm_kernel<1><<<grid, 192, TC_SMEM_BYTES, st>>>(a0h, a0l, a1h, a1l, bh, bl, p);
   if (launches) ++*launches;
   return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }

@@ -265,6 +265,7 @@ struct TG {
     p.m_tiles = (int)((M + TC_BM - 1) / TC_BM);
     const int chunks = W.rows / TC_NC;
     p.nch = 1; p.num_tiles = p.m_tiles * chunks; p.n_valid = W.rows; p.out_f32 = out; p.ldo = ldo; p.relumask = relumask; p.ldm = ldm;
+    p.chunk_minor = chunks; p.sa = 4; p.eg = 2;        // A (edge activations) streams from DRAM: four of the six stages
     if (tc_launch_maps(a0h, a0l, a1h, a1l, W.mh, W.ml, p, st, &h->launches)) err = fail(FD_ECUDA, "training tcgen05 GEMM launch failed: %s", cudaGetErrorString(cudaGetLastError()));
   }
   // planes out[M, W.rows] = relu([A0 | A1] W^T + bias + node terms), or — with `mask` — ([A0 | A1] W^T) where mask != 0 and 0 elsewhere (the
@@ -275,6 +276,7 @@ struct TG {
     TcGemmParams p{};
     p.M = (int)M; p.N = W.rows; p.KB0 = KB0; p.KB1 = 0; p.planes = 2; p.epi = TC_EPI_RELU; p.bias = bias;
     p.rowadd = rowadd; p.off_i = off_i; p.off_j = off_j; p.ld_rowadd = ET_NODE; p.nres = nres; p.out_hi = out_hi; p.out_lo = out_lo; p.maskplane = mask;
+    p.sa = 4; p.eg = 2;
     if (tc_launch_maps(a0h, a0l, a0h, a0l, W.mh, W.ml, p, st, &h->launches)) err = fail(FD_ECUDA, "training tcgen05 GEMM (planes) launch failed: %s", cudaGetErrorString(cudaGetLastError()));
   }
   void axis_sum_planes(const __nv_bfloat16* hi, const __nv_bfloat16* lo, float* out, long long R, int N, int Cc, int mode) {
@@ -303,6 +305,7 @@ struct TG {
     p.a_row_s0 = 0; p.a_row_s1 = 0; p.a_k_s1 = (int)(kb_per * TC_BK);
     p.b_row_s0 = 0; p.b_row_s1 = 0; p.b_k0 = 0; p.b_k_s1 = (int)(kb_per * TC_BK);
     p.o_s0 = 0; p.o_s1 = 0; p.n_valid = Cin; p.out_f32 = dW; p.ldo = lddw;
+    p.sa = p.nch == 1 ? 3 : 2;               // both operands stream from DRAM: one A block per nch B blocks
     if (tc_launch_maps(ah, al, ah, al, bh, bl, p, st, &h->launches)) err = fail(FD_ECUDA, "training tcgen05 weight-gradient launch failed: %s", cudaGetErrorString(cudaGetLastError()));
   }
   void copy(float* dst, int ldd, const float* src, int lds, int C, long long M, const float* rowmask = nullptr, bool accumulate = false) {
