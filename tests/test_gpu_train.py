@@ -219,3 +219,21 @@ def test_workspace_query_matches_allocations():
     Bt, Nt = batch["res_mask"].shape
     est, act = e2.lib.fd_workspace_bytes(e2._h, 2, Bt, Nt, 0, 0), e2.lib.fd_debug_alloc_bytes(e2._h, 2)
     assert act > 0 and abs(est - act) <= 0.03 * act, ("tape", est, act)
+
+
+def test_launch_count_covers_the_training_step():
+    """bench.py's `gpu_launches` of the training leg = fd_launch_count differences: forward, loss gradient, backward and Adam all count."""
+    e, g, batch, flat, grads = _setup("a", "tc")
+    feats = {k: batch[k] for k in FEAT_KEYS}
+    c0 = e.launch_count()
+    out = e.train_forward(feats)
+    c1 = e.launch_count()
+    dout = e.loss_backward(out, batch)
+    c2 = e.launch_count()
+    e.train_backward(dout)
+    c3 = e.launch_count()
+    m, v = torch.zeros_like(flat), torch.zeros_like(flat)
+    e.adam_step(flat, grads, m, v, lr=1e-4, step=1)
+    c4 = e.launch_count()
+    torch.cuda.synchronize()
+    assert c1 - c0 > 100 and c2 - c1 >= 2 and c3 - c2 > 100 and c4 - c3 == 1, (c0, c1, c2, c3, c4)
