@@ -1674,6 +1674,7 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 static PFN_encodeTiled g_encode = nullptr;
 static int g_tc_sms = 148;
+static int g_tc_sa = 0;             // FD_TC_SA=2|3|4 overrides the activation-ring depth of the launches that set one (A/B runs)
 static int g_tc_eg = 0;             // epilogue groups of tc_gemm_kernel: 0 = per launch (TcGemmParams::eg); FD_TC_EG=1|2 forces one variant (A/B runs)
 
 static long long* g_tc_prof = nullptr;   // device [32]; set by fd_debug_tc_profile
@@ -2045,6 +2046,7 @@ inline int tc_init(int sm_count) {
   g_encode = (PFN_encodeTiled)fn;
   if (cudaFuncSetAttribute(tc_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES) != cudaSuccess) return -2;
   if (cudaFuncSetAttribute(tc_gemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES) != cudaSuccess) return -2;
+  if (const char* e = getenv("FD_TC_SA")) { const int v = atoi(e); g_tc_sa = (v >= 2 && v <= 4) ? v : 0; }
   if (const char* e = getenv("FD_TC_EG")) g_tc_eg = atoi(e) == 2 ? 2 : (atoi(e) == 1 ? 1 : 0);
   if (cudaFuncSetAttribute(tc_edge_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FU_SMEM_BYTES) != cudaSuccess) return -2;
   if (cudaFuncSetAttribute(tc_edge_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FU_SMEM_BYTES) != cudaSuccess) return -2;
@@ -2242,6 +2244,7 @@ inline int tc_launch_maps(const CUtensorMap& a0h, const CUtensorMap& a0l, const 
     p.m_tiles = (p.M + TC_BM - 1) / TC_BM; p.nch = p.N / TC_NC; p.num_tiles = p.m_tiles; p.n_valid = p.N;
   }
   if (p.mma_n == 0) p.mma_n = TC_NC;
+  if (g_tc_sa && p.sa > 0) p.sa = g_tc_sa;
   const int grid = p.num_tiles < g_tc_sms ? p.num_tiles : g_tc_sms;
   if (g_tc_eg == 2 || (g_tc_eg == 0 && p.eg == 2)) tc_gemm_kernel<2><<<grid, 320, TC_SMEM_BYTES, st>>>(a0h, a0l, a1h, a1l, bh, bl, p);
   else tc_gemm_kernel<1><<<grid, 192, TC_SMEM_BYTES, st>>>(a0h, a0l, a1h, a1l, bh, bl, p);
