@@ -40,7 +40,7 @@ def parse():
     p.add_argument("--num-t", type=int, default=500)
     p.add_argument("--precision", default=None, choices=[None, "fp32", "bf16x3", "bf16"])
     p.add_argument("--no-cpu-baseline", action="store_true")
-    p.add_argument("--cpu-steps", type=int, default=2, help="denoise steps of the bounded CPU sample")
+    p.add_argument("--cpu-steps", type=int, default=14, help="denoise steps of the bounded CPU sample")
     p.add_argument("--mode", default="sample", choices=["sample", "train"],
                    help="sample (default, the headline metric) | train: one optimiser step (fwd + DSM loss + bwd + all-reduce + Adam), BASELINE config 4")
     p.add_argument("--sweep", action="store_true", help="measure the other BASELINE configs (C1 paper weights, C2, C5 length sweep) in one run")
@@ -193,7 +193,7 @@ def train_flops(B, N):
     return 3.0 * fwd * B
 
 
-def cpu_train_baseline(N, state):
+def cpu_train_baseline(N, state, steps=6):
     """The reference's training step on the host: autograd through the oracle port (forward + loss_fn + backward) + torch Adam, 1 example."""
     import torch
     from oracle import framediff_oracle as fo
@@ -209,13 +209,19 @@ def cpu_train_baseline(N, state):
              "trans_score_scaling": torch.tensor([fm["trans_score_scaling"]]), "res_mask": torch.ones(1, N, dtype=torch.float64),
              "fixed_mask": torch.zeros(1, N, dtype=torch.float64), "seq_idx": torch.arange(1, N + 1)[None],
              "torsion_angles_sin_cos": torch.tensor(tors)[None], "sc_ca_t": torch.zeros(1, N, 3, dtype=torch.float64), "t": torch.tensor([0.5], dtype=torch.float64)}
-    t0 = time.perf_counter()
-    out = fo.score_network_forward(w, batch, float_mask_quirk=True)
-    loss = fo.loss_terms(out, batch)["total_loss"]
-    opt.zero_grad(); loss.backward(); opt.step()
+    def one_step():
+        out = fo.score_network_forward(w, batch, float_mask_quirk=True)
+        loss = fo.loss_terms(out, batch)["total_loss"]
+        opt.zero_grad(); loss.backward(); opt.step()
+
+    one_step()                                       # untimed: first-touch allocations, thread pool start-up
+    n, t0 = 0, time.perf_counter()
+    while n < steps and (n == 0 or time.perf_counter() - t0 < 12.0):      # bounded sample: about 10 s of host work
+        one_step(); n += 1
     dt = time.perf_counter() - t0
-    return {"value": 1.0 / dt, "unit": "examples/s", "cores": torch.get_num_threads(), "kind": "port",
-            "sample": f"1 example x N={N}: forward + loss_fn + backward (torch autograd through the oracle port) + Adam in {dt:.2f} s",
+    return {"value": n / dt, "unit": "examples/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{n} steps of 1 example x N={N}: forward + loss_fn + backward (torch autograd through the oracle port) + Adam in {dt:.2f} s "
+                      f"(after one untimed step)",
             "seconds_measured": dt}
 
 
