@@ -1450,7 +1450,6 @@ extern "C" int fd_loss_backward(fd_handle h, int B, int N, const fd_loss_in* in,
   const size_t smem = (size_t)240 * N;
   if (smem > 200 * 1024) return fail(FD_EINVAL, "fd_loss_backward: N = %d too long", N);
   DevGuard dev_guard(h->device);
-  if (smem > 48 * 1024) CK(cudaFuncSetAttribute(loss_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   // number of samples with a non-empty mask (train_se3_diffusion.py:662) — a host value: the masks are inputs the caller just uploaded
   std::vector<float> hm((size_t)B * N);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -1553,7 +1552,6 @@ extern "C" int fd_loss_forward(fd_handle h, int B, int N, const fd_loss_in* in, 
   const size_t smem = (size_t)30 * N * sizeof(float);
   if (smem > 200 * 1024) return fail(FD_EINVAL, "fd_loss_forward: N = %d too long (pair-distance tile needs %zu bytes of shared memory)", N, smem);
   DevGuard dev_guard(h->device);
-  if (smem > 48 * 1024) CK(cudaFuncSetAttribute(loss_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   // per device
   LossArgs a{};
   a.pred_rot = in->pred_rot_score; a.pred_trans = in->pred_trans_score; a.pred_rigids = in->pred_rigids; a.pred_atom37 = in->pred_atom37;
   a.gt_rot = in->gt_rot_score; a.gt_trans = in->gt_trans_score; a.rot_scaling = in->rot_score_scaling; a.trans_scaling = in->trans_score_scaling;

@@ -1251,10 +1251,11 @@ __global__ void igso3_rows_post_kernel(const double* __restrict__ expv, const do
 
 
 // ----------------------------------------------------------------------------------------------------------------
-// DSM training loss, forward values (Experiment.loss_fn, experiments/train_se3_diffusion.py:538-660).  One CTA per sample:
+// DSM training loss, forward values (Experiment.loss_fn, experiments/train_se3_diffusion.py:538-660); kernels: loss_fwd2_kernel +
+// loss_finalize_kernel in fd_train.cuh.
 //   terms[b] = { rot_loss, trans_loss, bb_atom_loss, dist_mat_loss, their sum }   (the per-sample `batch_*` entries of aux_data)
 // Scores and their targets are fp64 (the reference's score tensors are), frames / atoms fp32 with fp64 accumulation; the ground-truth
-// backbone comes from rigids_0 and the psi torsion exactly as all_atom.compute_backbone builds it.  Dynamic smem: 2 x 5N x 3 floats.
+// backbone comes from rigids_0 and the psi torsion exactly as all_atom.compute_backbone builds it.
 // ----------------------------------------------------------------------------------------------------------------
 struct LossArgs {
   const double* pred_rot; const double* pred_trans; const float* pred_rigids; const float* pred_atom37;
@@ -1277,92 +1278,5 @@ __device__ __forceinline__ double block_sum_f64(double v, double* red) {   // 25
   return s;
 }
 
-__global__ void __launch_bounds__(256) loss_forward_kernel(const LossArgs a) {
-  extern __shared__ __align__(16) float lsm[];
-  const int N = a.N, b = blockIdx.x, tid = threadIdx.x;
-  float* gt5 = lsm;                 // [5N][3] ground-truth N, CA, C, CB, O
-  float* pr5 = lsm + 15 * N;        // [5N][3] predicted
-  __shared__ double red[8];
-  const double tb = a.t[b];
-  double s_trans_score = 0.0, s_trans_x0 = 0.0, s_axis = 0.0, s_angle = 0.0, s_rot = 0.0, s_mask = 0.0, s_bb = 0.0, s_bbm = 0.0;
-  for (int i = tid; i < N; i += 256) {
-    const long long r = (long long)b * N + i;
-    const double dm = 1.0 - (double)a.fixed_mask[r], lm = (double)a.res_mask[r] * dm;
-    s_mask += lm;
-    double ga = 0.0, pa = 0.0, g[3], q[3];
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      const double pt = a.pred_trans[r * 3 + k] * dm, dt = a.gt_trans[r * 3 + k] - pt;
-      s_trans_score += dt * dt * lm;
-      const double x0 = a.rigids_0[r * 7 + 4 + k] * a.coordinate_scaling - (double)a.pred_rigids[r * 7 + 4 + k] * a.coordinate_scaling;
-      s_trans_x0 += x0 * x0 * lm;
-      g[k] = a.gt_rot[r * 3 + k]; q[k] = a.pred_rot[r * 3 + k] * dm;
-      ga += g[k] * g[k]; pa += q[k] * q[k];
-      const double dr = g[k] - q[k];
-      s_rot += dr * dr * lm;
-    }
-    ga = sqrt(ga); pa = sqrt(pa);
-#pragma unroll
-    for (int k = 0; k < 3; ++k) { const double d = g[k] / (ga + 1e-6) - q[k] / (pa + 1e-6); s_axis += d * d * lm; }
-    s_angle += (ga - pa) * (ga - pa) * lm;
-    // ground-truth backbone of this residue (fp32, like compute_backbone on rigids_0.float()) and the predicted five atoms
-    float qf[4], R[9], tf[3], a37[111];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) qf[k] = (float)a.rigids_0[r * 7 + k];
-#pragma unroll
-    for (int k = 0; k < 3; ++k) tf[k] = (float)a.rigids_0[r * 7 + 4 + k];
-    quat_to_rot(qf, R);
-    backbone_atoms(R, tf, a.gt_psi[r * 2], a.gt_psi[r * 2 + 1], a37, nullptr);
-#pragma unroll
-    for (int at = 0; at < 5; ++at) {
-      const float mk = (fabsf(a37[at * 3]) + fabsf(a37[at * 3 + 1]) + fabsf(a37[at * 3 + 2])) != 0.f ? 1.f : 0.f;   // atom37_mask = any(pos != 0)
-#pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        const float pv = a.pred_atom37[(r * 37 + at) * 3 + k], gv = a37[at * 3 + k];
-        gt5[(i * 5 + at) * 3 + k] = gv; pr5[(i * 5 + at) * 3 + k] = pv;
-        const float df = pv - gv;
-        s_bb += (double)(df * df) * (double)mk * lm;
-      }
-      s_bbm += (double)mk * lm;
-    }
-  }
-  __syncthreads();
-  const double mask_sum = block_sum_f64(s_mask, red), denom = mask_sum + 1e-10;
-  const double trans_score = block_sum_f64(s_trans_score, red), trans_x0 = block_sum_f64(s_trans_x0, red);
-  const double axis = block_sum_f64(s_axis, red), angle = block_sum_f64(s_angle, red), rot = block_sum_f64(s_rot, red);
-  const double bb = block_sum_f64(s_bb, red), bbm = block_sum_f64(s_bbm, red);
-  // pairwise distances of the 5N atoms: mask = loss_mask[a] * res_mask[b] * (gt distance < 6 A); quirk: the sum is divided by (count - N)
-  double s_d = 0.0, s_dm = 0.0;
-  const int M = 5 * N;
-  for (long long pidx = tid; pidx < (long long)M * M; pidx += 256) {
-    const int x = (int)(pidx / M), y = (int)(pidx - (long long)x * M);
-    const long long rx = (long long)b * N + x / 5, ry = (long long)b * N + y / 5;
-    const float lmx = a.res_mask[rx] * (1.f - a.fixed_mask[rx]);
-    const float rmy = a.res_mask[ry];
-    const float gx = gt5[x * 3] - gt5[y * 3], gy = gt5[x * 3 + 1] - gt5[y * 3 + 1], gz = gt5[x * 3 + 2] - gt5[y * 3 + 2];
-    const float px = pr5[x * 3] - pr5[y * 3], py = pr5[x * 3 + 1] - pr5[y * 3 + 1], pz = pr5[x * 3 + 2] - pr5[y * 3 + 2];
-    const float gd = sqrtf(gx * gx + gy * gy + gz * gz) * lmx, pd = sqrtf(px * px + py * py + pz * pz) * lmx;
-    const double pm = (double)lmx * (double)rmy * (gd < 6.f ? 1.0 : 0.0);
-    const double dd = (double)gd - (double)pd;
-    s_d += dd * dd * pm; s_dm += pm;
-  }
-  const double dsum = block_sum_f64(s_d, red), dcnt = block_sum_f64(s_dm, red);
-  if (tid == 0) {
-    const double ts2 = a.trans_scaling[b] * a.trans_scaling[b], rs2 = a.rot_scaling[b] * a.rot_scaling[b];
-    double trans_loss = (tb > a.trans_x0_threshold ? (trans_score / ts2) / denom : 0.0) + (tb <= a.trans_x0_threshold ? trans_x0 / denom : 0.0);
-    trans_loss *= a.trans_loss_weight * (double)a.diffuse_trans;
-    double rot_loss;
-    if (a.separate_rot_loss) {
-      rot_loss = (angle / rs2) / denom * a.rot_loss_weight * (tb > a.rot_loss_t_threshold ? 1.0 : 0.0) + axis / denom;
-    } else {
-      rot_loss = (rot / rs2) / denom * a.rot_loss_weight * (tb > a.rot_loss_t_threshold ? 1.0 : 0.0);
-    }
-    rot_loss *= (double)a.diffuse_rot;
-    const double bb_loss = bb / (bbm + 1e-10) * a.bb_atom_loss_weight * (tb < a.bb_atom_loss_t_filter ? 1.0 : 0.0) * a.aux_loss_weight;
-    const double dm_loss = dsum / (dcnt - (double)N) * a.dist_mat_loss_weight * (tb < a.dist_mat_loss_t_filter ? 1.0 : 0.0) * a.aux_loss_weight;
-    double* o = a.terms + (long long)b * 5;
-    o[0] = rot_loss; o[1] = trans_loss; o[2] = bb_loss; o[3] = dm_loss; o[4] = ((rot_loss + trans_loss) + bb_loss) + dm_loss;
-  }
-}
 
 }  // namespace fd

@@ -1557,27 +1557,6 @@ __global__ void vt_planes_kernel(const float* __restrict__ x, int ld, int col0, 
   }
 }
 
-// fp32 [M, ld] (first C columns) -> TRANSPOSED bf16 hi/lo planes [Cp rows, Kp] (row c = channel c, column = row index of x), zeros for rows of x
-// beyond M and channels beyond C: the K-major operands of a weight gradient dW = dy^T x contracted over the rows (training path).
-__global__ void tsplit_planes_kernel(const float* __restrict__ x, int ld, long long M, int C, long long Kp, __nv_bfloat16* __restrict__ hi,
-                                     __nv_bfloat16* __restrict__ lo) {
-  __shared__ float tile[64][33];
-  const long long j0 = (long long)blockIdx.x * 64;
-  const int c0 = blockIdx.y * 32;
-  const int tx = threadIdx.x, ty = threadIdx.y;   // 32 x 8
-  for (int r = ty; r < 64; r += 8) {
-    const long long j = j0 + r;
-    tile[r][tx] = (j < M && c0 + tx < C) ? x[j * ld + c0 + tx] : 0.f;
-  }
-  __syncthreads();
-  for (int r = ty; r < 32; r += 8) {              // channel c0 + r: lane tx writes the row pair (j0 + 2 tx, j0 + 2 tx + 1)
-    uint32_t h2, l2;
-    split2_bf16(tile[2 * tx][r], tile[2 * tx + 1][r], h2, l2);
-    const long long o = (long long)(c0 + r) * Kp + j0 + 2 * tx;
-    *reinterpret_cast<uint32_t*>(hi + o) = h2;
-    *reinterpret_cast<uint32_t*>(lo + o) = l2;
-  }
-}
 // Per-head zero-padded split of the sequence transformer's q and k:  out[m, g*dhp + c] = x[m*ld + g*dh + c] (c < dh), 0 otherwise,
 // for the ngroups = 2*heads consecutive dh-wide groups (q heads then k heads).  K-blocks of 64 then never straddle two heads.
 __global__ void split_heads_pad_kernel(const float* __restrict__ x, int ld, long long M, int ngroups, int dh, int dhp,

@@ -19,10 +19,6 @@ __global__ void zero_f32_kernel(float* __restrict__ p, long long n) {
   if (i + 3 < n) *reinterpret_cast<float4*>(p + i) = make_float4(0.f, 0.f, 0.f, 0.f);
   else for (long long k = i; k < n; ++k) p[k] = 0.f;
 }
-__global__ void add_f32_kernel(float* __restrict__ dst, const float* __restrict__ src, long long n) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) dst[i] += src[i];
-}
 // dst[m][0:C] (ld ldd) (+)= src[m][0:C] (ld lds) * (rowmask ? rowmask[m] : 1)
 __global__ void copy_cols_kernel(float* __restrict__ dst, int ldd, const float* __restrict__ src, int lds, int C, long long M,
                                  const float* __restrict__ rowmask, int accumulate) {
@@ -904,8 +900,8 @@ __global__ void __launch_bounds__(256) score_head_bwd_kernel(const HeadBwdArgs a
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// DSM loss backward (forward: loss_forward_kernel; train_se3_diffusion.py:538-680): gradient of total_loss = sum_b batch_loss[b] /
-// (#samples with any residue + 1e-10) w.r.t. the model outputs.  One CTA per sample.
+// DSM loss backward (train_se3_diffusion.py:538-680): gradient of total_loss = sum_b batch_loss[b] /
+// (#samples with any residue + 1e-10) w.r.t. the model outputs (kernels: loss_count_kernel + loss_bwd2_kernel below).
 //   d_rot [B,N,3] f64, d_trans [B,N,3] f64, d_rigids [B,N,7] f32 (only the translation part is non-zero), d_atom37 [B,N,37,3] f32
 // ---------------------------------------------------------------------------------------------------------------------
 struct LossBwdArgs {
@@ -930,157 +926,10 @@ __device__ __forceinline__ double block_sum_f64_t(double v, double* red) {   // 
   for (int w = 0; w < 8; ++w) s += red[w];
   return s;
 }
-__global__ void __launch_bounds__(256) loss_backward_kernel(const LossBwdArgs a) {
-  extern __shared__ __align__(16) float lsm[];
-  __shared__ double red[8];
-  const int N = a.N, b = blockIdx.x, tid = threadIdx.x;
-  float* gt5 = lsm;                 // [5N][3]
-  float* pr5 = gt5 + 15 * N;        // [5N][3]
-  double* dacc = reinterpret_cast<double*>(pr5 + 15 * N);   // [5N][3] gradient accumulators of the pair term (fp64)
-  const double tt = a.t[b];
-  const long long r0 = (long long)b * N;
-  // per-sample denominators
-  double lm_sum = 0.0;
-  for (int n = tid; n < N; n += 256) lm_sum += (double)(a.res_mask[r0 + n] * (1.f - a.fixed_mask[r0 + n]));
-  lm_sum = block_sum_f64_t(lm_sum, red);
-  const double denom = lm_sum + 1e-10;
-  const double ws = a.inv_nvalid;
-  // ---- ground-truth / predicted backbone atoms into shared memory (5 atoms per residue) ----
-  double bm_sum = 0.0;
-  for (int n = tid; n < N; n += 256) {
-    float q[4], R[9], t3[3], a37[111];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) q[k] = (float)a.rigids_0[(r0 + n) * 7 + k];
-#pragma unroll
-    for (int k = 0; k < 3; ++k) t3[k] = (float)a.rigids_0[(r0 + n) * 7 + 4 + k];
-    quat_to_rot(q, R);
-    backbone_atoms(R, t3, a.gt_psi[(r0 + n) * 2], a.gt_psi[(r0 + n) * 2 + 1], a37, nullptr);
-    const float lm = a.res_mask[r0 + n] * (1.f - a.fixed_mask[r0 + n]);
-#pragma unroll
-    for (int k = 0; k < 15; ++k) {
-      gt5[n * 15 + k] = a37[k];
-      pr5[n * 15 + k] = a.pred_atom37[(r0 + n) * 111 + k];
-      dacc[n * 15 + k] = 0.0;
-    }
-#pragma unroll
-    for (int at = 0; at < 5; ++at) {
-      const bool present = a37[at * 3] != 0.f || a37[at * 3 + 1] != 0.f || a37[at * 3 + 2] != 0.f;
-      if (present) bm_sum += (double)lm;
-    }
-  }
-  bm_sum = block_sum_f64_t(bm_sum, red);
-  __syncthreads();
-  // ---- per-residue terms: rotation, translation, backbone atoms ----
-  const double hi_t = tt > a.trans_x0_threshold ? 1.0 : 0.0;
-  const double wa = a.rot_loss_weight * (tt > a.rot_loss_t_threshold ? 1.0 : 0.0);
-  const double w_bb = a.bb_atom_loss_weight * (tt < a.bb_atom_loss_t_filter ? 1.0 : 0.0) * a.aux_loss_weight;
-  const double rsc = a.rot_scaling[b], tsc = a.trans_scaling[b];
-  for (int n = tid; n < N; n += 256) {
-    const long long r = r0 + n;
-    const double dmk = 1.0 - (double)a.fixed_mask[r];
-    const double lm = (double)a.res_mask[r] * dmk;
-    // translation
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      const double e = a.gt_trans[r * 3 + k] - a.pred_trans[r * 3 + k] * dmk;
-      a.d_trans[r * 3 + k] = a.diffuse_trans ? -2.0 * e * lm / (tsc * tsc * denom) * (hi_t * a.trans_loss_weight * ws) * dmk : 0.0;
-      const double x0g = a.rigids_0[r * 7 + 4 + k] * a.coordinate_scaling, x0p = (double)a.pred_rigids[r * 7 + 4 + k] * a.coordinate_scaling;
-      const double dx0 = a.diffuse_trans ? -2.0 * (x0g - x0p) * lm / denom * ((1.0 - hi_t) * a.trans_loss_weight * ws) * a.coordinate_scaling : 0.0;
-      a.d_rigids[r * 7 + 4 + k] = (float)dx0;
-    }
-#pragma unroll
-    for (int k = 0; k < 4; ++k) a.d_rigids[r * 7 + k] = 0.f;
-    // rotation
-    double pr[3], gr[3], pa = 0.0, ga = 0.0;
-#pragma unroll
-    for (int k = 0; k < 3; ++k) { pr[k] = a.pred_rot[r * 3 + k] * dmk; gr[k] = a.gt_rot[r * 3 + k]; pa += pr[k] * pr[k]; ga += gr[k] * gr[k]; }
-    pa = sqrt(pa); ga = sqrt(ga);
-    double dpr[3];
-    if (a.separate_rot_loss) {
-      double dpax[3], dotp = 0.0;
-#pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        dpax[k] = -2.0 * (gr[k] / (ga + 1e-6) - pr[k] / (pa + 1e-6)) * lm / denom * ws;
-        dotp += dpax[k] * pr[k];
-      }
-      const double dpa = -2.0 * (ga - pa) * lm / (rsc * rsc * denom) * (wa * ws);
-      const double ipa_ = 1.0 / fmax(pa, 1e-30);
-#pragma unroll
-      for (int k = 0; k < 3; ++k) dpr[k] = dpax[k] / (pa + 1e-6) - dotp / ((pa + 1e-6) * (pa + 1e-6)) * pr[k] * ipa_ + dpa * pr[k] * ipa_;
-    } else {
-#pragma unroll
-      for (int k = 0; k < 3; ++k) dpr[k] = -2.0 * (gr[k] - pr[k]) * lm / (rsc * rsc * denom) * (wa * ws);
-    }
-#pragma unroll
-    for (int k = 0; k < 3; ++k) a.d_rot[r * 3 + k] = a.diffuse_rot ? dpr[k] * dmk : 0.0;
-    // backbone atoms
-#pragma unroll
-    for (int at = 0; at < 5; ++at) {
-      const float* g = gt5 + n * 15 + at * 3;
-      const bool present = g[0] != 0.f || g[1] != 0.f || g[2] != 0.f;
-      const double bm = present ? lm : 0.0;
-#pragma unroll
-      for (int k = 0; k < 3; ++k)
-        dacc[n * 15 + at * 3 + k] = 2.0 * ((double)pr5[n * 15 + at * 3 + k] - (double)g[k]) * bm / (bm_sum + 1e-10) * (w_bb * ws);
-    }
-  }
-  __syncthreads();
-  // ---- pairwise distances of the 5N atoms: pairs with gt distance < 6 A ----
-  const double w_dm = a.dist_mat_loss_weight * (tt < a.dist_mat_loss_t_filter ? 1.0 : 0.0) * a.aux_loss_weight;
-  if (w_dm != 0.0) {
-    const int M5 = 5 * N;
-    // pass 1: the denominator sum(pair_mask) - N
-    double pm_sum = 0.0;
-    for (int p = tid; p < M5; p += 256) {
-      const int n = p / 5;
-      const float fl = a.res_mask[r0 + n] * (1.f - a.fixed_mask[r0 + n]);
-      if (fl == 0.f) continue;
-      const float gx = gt5[p * 3], gy = gt5[p * 3 + 1], gz = gt5[p * 3 + 2];
-      for (int qx = 0; qx < M5; ++qx) {
-        const float fr = a.res_mask[r0 + qx / 5];
-        const float ex = gx - gt5[qx * 3], ey = gy - gt5[qx * 3 + 1], ez = gz - gt5[qx * 3 + 2];
-        const float gd = sqrtf(ex * ex + ey * ey + ez * ez) * fl;
-        if (gd < 6.f) pm_sum += (double)(fl * fr);
-      }
-    }
-    pm_sum = block_sum_f64_t(pm_sum, red);
-    const double pden = pm_sum - (double)N;
-    // pass 2: gradient; thread p owns row p (adds +coef*diff), and the symmetric -coef*diff lands on column q through atomics
-    for (int p = tid; p < M5; p += 256) {
-      const int n = p / 5;
-      const float fl = a.res_mask[r0 + n] * (1.f - a.fixed_mask[r0 + n]);
-      if (fl == 0.f) continue;
-      const float gx = gt5[p * 3], gy = gt5[p * 3 + 1], gz = gt5[p * 3 + 2];
-      const float px = pr5[p * 3], py = pr5[p * 3 + 1], pz = pr5[p * 3 + 2];
-      double ax = 0.0, ay = 0.0, az = 0.0;
-      for (int qx = 0; qx < M5; ++qx) {
-        const float fr = a.res_mask[r0 + qx / 5];
-        const float ex = gx - gt5[qx * 3], ey = gy - gt5[qx * 3 + 1], ez = gz - gt5[qx * 3 + 2];
-        const float gd = sqrtf(ex * ex + ey * ey + ez * ez) * fl;
-        if (!(gd < 6.f) || fr == 0.f) continue;
-        const float dxp = px - pr5[qx * 3], dyp = py - pr5[qx * 3 + 1], dzp = pz - pr5[qx * 3 + 2];
-        const float pdr = sqrtf(dxp * dxp + dyp * dyp + dzp * dzp);
-        if (!(pdr > 0.f)) continue;
-        const double pd = (double)pdr * (double)fl;
-        const double coef = -2.0 * ((double)gd - pd) * (double)(fl * fr) / pden * (w_dm * ws) * (double)fl / (double)pdr;
-        ax += coef * dxp; ay += coef * dyp; az += coef * dzp;
-        atomicAdd(&dacc[qx * 3 + 0], -coef * (double)dxp);
-        atomicAdd(&dacc[qx * 3 + 1], -coef * (double)dyp);
-        atomicAdd(&dacc[qx * 3 + 2], -coef * (double)dzp);
-      }
-      atomicAdd(&dacc[p * 3 + 0], ax); atomicAdd(&dacc[p * 3 + 1], ay); atomicAdd(&dacc[p * 3 + 2], az);
-    }
-    __syncthreads();
-  }
-  for (int idx = tid; idx < N * 111; idx += 256) {
-    const int n = idx / 111, k = idx - n * 111;
-    a.d_atom37[(r0 + n) * 111 + k] = k < 15 ? (float)dacc[n * 15 + k] : 0.f;
-  }
-}
 
 // ---------------------------------------------------------------------------------------------------------------------
-// DSM loss, version 2: the same arithmetic as loss_forward_kernel / loss_backward_kernel spread over grid (B, slabs) — the
-// 5N x 5N pair loop of ONE CTA per example was 6 % of a training step at B = 8.  Every CTA stages the example's ground-truth and
+// DSM loss kernels: the arithmetic of Experiment.loss_fn spread over grid (B, slabs) — with ONE CTA per example the 5N x 5N pair loop
+// was 6 % of a training step at B = 8.  Every CTA stages the example's ground-truth and
 // predicted backbone atoms in shared memory (cheap, O(N)) and owns LOSS_RES residues: their per-residue terms and their 5*LOSS_RES
 // rows of the pair matrix.  Forward: partial sums -> atomicAdd(double) into acc[b][10], a second tiny kernel forms the terms.
 // Backward: the pair denominator comes from a counting launch; row p's gradient is sum_q (c_pq + c_qp)(x_p - x_q) — both ordered pairs
