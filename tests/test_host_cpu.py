@@ -246,3 +246,31 @@ def test_linear_initialisers_follow_the_reference_distribution():
     assert float(lin.weight.abs().max()) == 0.0
     with pytest.raises(ValueError):
         _Linear(4, 4, "nonsense")
+
+
+@pytest.mark.parametrize("mode", ["sample", "train"])
+def test_bench_reference_arm_contract(mode):
+    """`bench.py --impl reference` (the CPU arm the driver times next to the product): runs without the product library, prints ONE JSON line with
+    the contract's keys, e2e repeating the line's own value, and a cpu_baseline block describing the bounded sample."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    # run in-process-of-the-child through runpy so the child can inspect its own address space afterwards: the product library must not be mapped
+    prog = ("import runpy, sys; sys.argv = ['bench.py', '--impl', 'reference', '--mode', '%s', '--steps', '1', '--warmup', '0', '--nres', '24', "
+            "'--num-t', '12']; runpy.run_path('bench.py', run_name='__main__'); "
+            "assert 'libframediff' not in open('/proc/self/maps').read(), 'reference arm mapped the product library'" % mode)
+    cmd = [sys.executable, "-c", prog]
+    env = dict(os.environ, OMP_NUM_THREADS="8")
+    res = subprocess.run(cmd, cwd=root, env=env, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stderr[-2000:]
+    lines = [l for l in res.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1, res.stdout[-2000:]
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["gpu_launches"] == 0 and d["higher_is_better"] is True and d["value"] > 0
+    assert d["unit"] == ("residues/s" if mode == "sample" else "examples/s")
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
+    if mode == "sample":
+        assert "10 of 12 denoise steps" in cb["sample"]          # at least 10 denoise steps per bounded sample (SURVEY §8(d))
