@@ -46,7 +46,7 @@ def parse():
     p.add_argument("--sweep", action="store_true", help="measure the other BASELINE configs (C1 paper weights, C2, C5 length sweep) in one run")
     p.add_argument("--lr", type=float, default=1e-4)
     p.add_argument("--train-gemm", default="tc", choices=["fp32", "bf16x3", "tc"],
-                   help="training-path GEMMs: CUDA-core fp32 | split-bf16 mma.sync | split-bf16 with the edge-tensor forward/dgrad GEMMs on tcgen05")
+                   help="training-path GEMMs: CUDA-core fp32 | split-bf16 mma.sync | split-bf16 with the edge-tensor GEMMs (forward, data and weight gradients) on tcgen05")
     return p.parse_args()
 
 
@@ -300,7 +300,7 @@ def run_train(args):
                 "e2e": {"value": world * B / e2e_s, "unit": "examples/s", "ms_per_step": e2e_s * 1e3, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8},
                 "comm_exposed_ms_per_step": exposed_ms, "allreduce_bytes_per_step": int(ts.grads.numel() * 4) if world > 1 else 0,
                 "final_loss": losses[-1] if losses else None, "clocks": clk, "gpu_launches": int(launches),
-                "roofline": {"bound": "tensor", "kernel": "whole training step (forward + dgrad + wgrad GEMMs: %s)" % {"fp32": "fp32 CUDA cores", "bf16x3": "mm3_kernel, mma.sync split-bf16", "tc": "edge-tensor forward/dgrad on tc_gemm_kernel (tcgen05), weight gradients and node path on mm3_kernel (mma.sync); split-bf16"}[args.train_gemm],
+                "roofline": {"bound": "tensor", "kernel": "whole training step (forward + dgrad + wgrad GEMMs: %s)" % {"fp32": "fp32 CUDA cores", "bf16x3": "mm3_kernel, mma.sync split-bf16", "tc": "edge-tensor forward / dgrad / wgrad on tc_gemm_kernel (tcgen05), node path and small weight gradients on mm3_kernel (mma.sync); split-bf16"}[args.train_gemm],
                              "achieved": ach, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": ach / pk["bf16_tflops_sustained"],
                              "peak_source": pk["source"], "traffic": None, "executed_flops_per_step": fl},
                 "cpu_baseline": cb}
